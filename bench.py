@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""users/sec of CDAE training (BASELINE.json metric) on N B200s, plus the CPU reference arm.
+
+A step = ONE EPOCH (CDAE::train_one_iteration, cdae.hpp:136-146) over the synthetic config-B
+set: 100,000 users x 50,000 items per GPU (weak scaling: U = 100,000 * N), ~30 train items per
+user, K=50, num_neg=5, q=0.5 scaled, CROSS_ENTROPY, lambda=.01, lr=.1, AdaGrad beta=1, tied
+weights, user factor on.  `value` times the epoch with the CSR resident in HBM
+(CUDA events on the engine's stream); `e2e` times cdae_train_epoch_csr, which takes the CSR from
+pinned HOST memory on every call and reads the epoch statistics back.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (torchrun for N > 1)
+  python bench.py --impl reference ...   the reference's own CPU path (oracle/_ref)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "users/sec CDAE training (K=50, Yelp-scale)"
+UNIT = "users/s"
+USERS_PER_GPU = 100_000
+ITEMS = 50_000
+MEAN_ITEMS = 30.0
+K, NUM_NEG = 50, 5
+SEED = 20141119
+
+MODEL_CFG = dict(lambda_=0.01, learn_rate=0.1, corruption_ratio=0.5, beta=1.0, loss="CE",
+                 num_dim=K, num_neg=NUM_NEG, num_corruptions=1, using_adagrad=True,
+                 asymmetric=False, user_factor=True, linear=False, scaled=True,
+                 linear_function=False, tanh=False)
+
+
+def workload_name(n_gpus):
+    return ("synthetic %dK users x %dK items, K=%d, neg-sample=%d, %dxB200"
+            % (USERS_PER_GPU * n_gpus // 1000, ITEMS // 1000, K, NUM_NEG, n_gpus))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_reference_rate(data, n_sample, steps=1, warmup=0, quiet=True):
+    """users/s of the reference's own (single-threaded, fp64) train loop on the first n_sample
+    users.  Uses oracle/_ref (the verbatim reference headers) when that library exists, else the
+    C port.  Returns (value, info)."""
+    from oracle import oracle as orc
+    rp, col = data["train_row_ptr"], data["train_col"]
+    n = int(min(n_sample, data["U"]))
+    sub_rp = np.ascontiguousarray(rp[:n + 1])
+    sub_col = np.ascontiguousarray(col[:rp[n]])
+    if orc.have_reference():
+        col2, i_seen = orc.first_seen_relabel(sub_rp, sub_col)
+        ref = orc.Reference(MODEL_CFG, n, i_seen, sub_rp, col2, quiet=quiet)
+        orc.Reference.seed(SEED, SEED)
+        times = [ref.train_user_range(0, n) for _ in range(warmup + steps)][warmup:]
+        kind = "reference"
+        how = ("verbatim reference headers (oracle/_ref, Eigen/Boost/glog stand-ins), first %d of "
+               "%d users, %d of %d items seen, 1 thread (the reference trains single-threaded)"
+               % (n, data["U"], i_seen, data["I"]))
+    else:
+        o = orc.Oracle(MODEL_CFG, data["U"], data["I"], rp, col)
+        o.init_params(SEED)
+        times = []
+        for s in range(warmup + steps):
+            t = time.perf_counter()
+            o.train_epoch(SEED, s, 1, 0, n)
+            times.append(time.perf_counter() - t)
+        times = times[warmup:]
+        kind = "port"
+        how = "C port of the reference loop (oracle/), first %d of %d users, 1 thread" % (n, data["U"])
+    return n * len(times) / sum(times), dict(kind=kind, cores=1, sample=how), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from cdae_b200 import synth
+    from oracle import oracle as orc
+    orc.build(ref=False)
+    data = synth.make_dataset(USERS_PER_GPU, ITEMS, MEAN_ITEMS, seed=SEED)
+    # calibrate so that the whole (warmup + steps) run stays within ~2 minutes
+    rate, _, _ = cpu_reference_rate(data, 1000)
+    total = max(1, args.steps + args.warmup)
+    n = int(max(500, min(USERS_PER_GPU, rate * 120.0 / total)))
+    value, info, times = cpu_reference_rate(data, n, args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    info["value"] = value
+    info["unit"] = UNIT
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(1), "sample_users_per_step": n},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cdae_b200 import CDAE, CDAEConfig, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    U = USERS_PER_GPU * world
+    data = synth.make_dataset(U, ITEMS, MEAN_ITEMS, seed=SEED)   # same arrays on every rank
+    rp, col = data["train_row_ptr"], data["train_col"]
+    batch_users = args.batch_users * world                        # global minibatch, weak scaling
+    m = CDAE(CDAEConfig(batch_users=batch_users, device=local, **MODEL_CFG)).reset(U, ITEMS, rp, col)
+    if world > 1:
+        uid = [CDAE.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        m.dist_init(rank, world, uid[0])
+    m.init_params(SEED)
+    rp_pin, col_pin = m.pinned_array(rp), m.pinned_array(col)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        m.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_epoch(epoch, host_csr):
+        flush.zero_()                       # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        st = m.train_one_iteration(seed=SEED, epoch=epoch,
+                                   csr=(rp_pin, col_pin) if host_csr else None)
+        return st, time.perf_counter() - t
+
+    epoch = 0
+    for _ in range(args.warmup):
+        one_epoch(epoch, False)
+        epoch += 1
+    # ---- timed region 1: CSR resident in HBM, device time (CUDA events on the engine stream)
+    m.profile(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches, outputs, users = 0.0, 0, 0, 0
+    loss = 0.0
+    for _ in range(args.steps):
+        st, _w = one_epoch(epoch, False)
+        epoch += 1
+        dev_ms += st.device_ms
+        launches += st.kernel_launches
+        outputs += st.outputs
+        users += st.user_steps
+        loss = st.loss_sum
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    prof = m.profile_get()
+    m.profile(False)
+    # ---- timed region 2: end to end through the host-CSR call (wall clock incl. H2D + D2H)
+    for _ in range(min(2, args.warmup)):
+        one_epoch(epoch, True)
+        epoch += 1
+    barrier()
+    e2e_s, h2d, d2h = 0.0, 0, 0
+    for _ in range(args.steps):
+        st, w = one_epoch(epoch, True)
+        epoch += 1
+        e2e_s += w
+        h2d, d2h = st.h2d_bytes, st.d2h_bytes
+    barrier()
+
+    tv = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([users, outputs, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)       # max over ranks
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = tv.tolist()
+    users_all, outputs_all, launches_all = cnt.tolist()
+    if rank == 0:
+        value = users_all / (dev_ms / 1e3)
+        e2e = users_all / (e2e_ms / 1e3)
+        peak, peak_src = measured_peaks()
+        # dominant kernel: sampled decode.  Algorithmic bytes:
+        # outputs * (P*4K + P*4 + 4), P = 4 row passes with AdaGrad.
+        dec_ms, dec_n = prof["decode"]
+        P = 4 if MODEL_CFG["using_adagrad"] else 2
+        out_rank0 = outputs_all / world
+        alg_bytes = out_rank0 * (P * 4 * K + P * 4 + 4)
+        achieved = alg_bytes / (dec_ms / 1e3) / 1e9 if dec_ms > 0 else None
+        roofline = {"bound": "hbm", "kernel": "decode_kernel<16,1,true>", "achieved": achieved,
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak if achieved else None, "traffic": None,
+                    "launches": dec_n, "avg_launch_ms": dec_ms / dec_n if dec_n else None,
+                    "algorithmic_bytes_per_launch": alg_bytes / dec_n if dec_n else None,
+                    "kernel_ms_share": {k: v[0] / dev_ms for k, v in prof.items() if v[1]}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload_name(world), "users": U, "items": ITEMS,
+                           "train_nnz": int(len(col)), "batch_users": batch_users,
+                           "step": "one epoch = CDAE::train_one_iteration over all users",
+                           "l2": "256 MB flush write between timed iterations",
+                           "parallelism": "dp%d (users sharded, 1 all-reduce of dense item gradients per minibatch)" % world,
+                           "loss_last_epoch": loss},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            orc.build(ref=False)
+            v, info, _ = cpu_reference_rate(data, args.cpu_sample)
+            info["value"] = v
+            info["unit"] = UNIT
+            line["cpu_baseline"] = info
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-users", type=int, default=8192, help="users per minibatch per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=30000,
+                    help="users in the bounded CPU-baseline sample (about 10-15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,885 @@
+// cdae_b200/csrc/api.cu — the extern "C" layer of include/cdae_b200.h: owns device memory,
+// builds the per-minibatch work lists, queues the kernels of train_kernels.cuh /
+// topn_kernels.cuh on one stream, and (optionally) all-reduces the dense gradients with NCCL.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cdae_b200.h"
+#include "handle.cuh"
+#include "topn_kernels.cuh"
+#include "train_kernels.cuh"
+
+using namespace cdae;
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_last_error;
+
+int cdae::set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return set_error(CDAE_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                       __FILE__, __LINE__);                                                   \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int rc__ = (call);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+#define KERNEL_OK(h)                                                                   \
+  do {                                                                                 \
+    ++(h)->launches;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess)                                                            \
+      return set_error(CDAE_E_CUDA, "kernel launch failed: %s (%s:%d)",                \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Optional per-kernel-class device timing (cdae_profile): an event pair around every launch of
+// the class, summed after the call's final synchronise.  Off by default (no events recorded).
+struct ProfScope {
+  cdae_handle* h;
+  int cls;
+  ProfScope(cdae_handle* h_, int cls_) : h(h_), cls(cls_) {
+    if (h->profiling) h->prof_begin(cls);
+  }
+  ~ProfScope() {
+    if (h->profiling) h->prof_end();
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so a single-GPU process never needs it
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclFloat = 7, kNcclSum = 0;
+
+int load_nccl() {
+  if (g_nccl.lib) return 0;
+  // prefer a copy that is already mapped (torch bundles one), then the system library
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return set_error(CDAE_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return set_error(CDAE_E_NCCL, "libnccl.so.2 lacks the expected symbols");
+  g_nccl.lib = lib;
+  return 0;
+}
+#define NC(call)                                                                               \
+  do {                                                                                         \
+    int r__ = (call);                                                                          \
+    if (r__ != 0)                                                                              \
+      return set_error(CDAE_E_NCCL, "%s failed: %s", #call,                                    \
+                       g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?");              \
+  } while (0)
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// handle helpers
+static int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+static float* param_ptr(cdae_handle* h, int which, int64_t* rows, int64_t* cols, int* ldp) {
+  ModelDev& m = h->m;
+  float* p = nullptr;
+  int64_t r = 0, c = h->K;
+  int ld = h->ld;
+  switch (which) {
+    case CDAE_P_W: p = m.W; r = h->I; break;
+    case CDAE_P_W_AG: p = m.W_ag; r = h->I; break;
+    case CDAE_P_V: p = m.V; r = m.V ? h->I : 0; break;
+    case CDAE_P_V_AG: p = m.V_ag; r = m.V_ag ? h->I : 0; break;
+    case CDAE_P_WU: p = m.Wu; r = m.Wu ? h->U : 0; break;
+    case CDAE_P_WU_AG: p = m.Wu_ag; r = m.Wu_ag ? h->U : 0; break;
+    case CDAE_P_UU: p = m.Uu; r = m.Uu ? h->U : 0; break;
+    case CDAE_P_UU_AG: p = m.Uu_ag; r = m.Uu_ag ? h->U : 0; break;
+    // vectors are stored as ONE padded row (b: [ld]) or a plain array (b': [I])
+    case CDAE_P_B: p = m.b; r = 1; c = h->K; break;
+    case CDAE_P_B_AG: p = m.b_ag; r = 1; c = h->K; break;
+    case CDAE_P_BPRIME: p = m.bp; r = 1; c = h->I; ld = (int)h->I; break;
+    case CDAE_P_BPRIME_AG: p = m.bp_ag; r = 1; c = h->I; ld = (int)h->I; break;
+    default: return nullptr;
+  }
+  if (r == 0) c = 0;
+  *rows = r; *cols = c; *ldp = ld;
+  return p;
+}
+
+static int alloc_table(cdae_handle* h, float** p, int64_t rows, int K, int ld, float fill) {
+  CU(cudaMalloc(p, sizeof(float) * (size_t)std::max<int64_t>(rows * ld, 4)));
+  h->dev_bytes += sizeof(float) * (size_t)(rows * ld);
+  if (rows * ld > 0) {
+    fill_kernel<<<cdiv(rows * ld, 256), 256, 0, h->stream>>>(*p, rows, K, ld, fill);
+    KERNEL_OK(h);
+  }
+  return 0;
+}
+
+template <class T>
+static int ensure(cdae_handle* h, DevBuf<T>& b, size_t n) {
+  if (b.cap >= n && b.p) return 0;
+  if (b.p) CU(cudaFree(b.p));
+  b.p = nullptr;
+  size_t cap = std::max<size_t>(n + n / 4, 256);
+  CU(cudaMalloc(&b.p, cap * sizeof(T)));
+  b.cap = cap;
+  (void)h;
+  return 0;
+}
+
+// Chunk the rows of `users` (global ids, in the order given) into warp work items.
+// aux offsets count slots from the first listed user, u_local counts users from it.
+static void build_items(const int64_t* row_ptr, const int64_t* users, int64_t n_users,
+                        int64_t uid_base, int ch_in, int ch_out, std::vector<WorkItem>* in,
+                        std::vector<WorkItem>* out, int64_t* total_slots) {
+  int64_t aux = 0;
+  for (int64_t i = 0; i < n_users; ++i) {
+    const int64_t uid = users ? users[i] : uid_base + i;
+    const int64_t s0 = row_ptr[uid], n = row_ptr[uid + 1] - s0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int ch = pass == 0 ? ch_in : ch_out;
+      std::vector<WorkItem>* dst = pass == 0 ? in : out;
+      if (!dst) continue;
+      for (int64_t o = 0; o < n; o += ch) {
+        WorkItem w;
+        w.uid = (int32_t)uid;
+        w.u_local = (int32_t)i;
+        w.n = (int32_t)std::min<int64_t>(ch, n - o);
+        w.aux0 = (int32_t)(aux + o);
+        w.s0 = s0 + o;
+        w.first = o == 0;
+        w.row_off = (int32_t)o;
+        dst->push_back(w);
+      }
+    }
+    aux += n;
+  }
+  if (total_slots) *total_slots = aux;
+}
+
+static int validate_csr(int64_t U, int64_t I, const int64_t* rp, const int32_t* col) {
+  if (rp[0] != 0) return set_error(CDAE_E_INVALID, "row_ptr[0] must be 0");
+  for (int64_t u = 0; u < U; ++u) {
+    if (rp[u + 1] < rp[u]) return set_error(CDAE_E_INVALID, "row_ptr not monotone at user %lld", (long long)u);
+    for (int64_t s = rp[u]; s < rp[u + 1]; ++s) {
+      if (col[s] < 0 || col[s] >= I)
+        return set_error(CDAE_E_INVALID, "item id %d of user %lld outside [0,%lld)", col[s], (long long)u, (long long)I);
+      if (s > rp[u] && col[s - 1] >= col[s])
+        return set_error(CDAE_E_INVALID, "row of user %lld is not strictly ascending", (long long)u);
+    }
+  }
+  return 0;
+}
+
+// (Re)build the epoch plan: this rank's slice of every global minibatch, as contiguous ranges
+// of one work-item list.  Depends on row_ptr only.
+static int build_plan(cdae_handle* h) {
+  const int64_t B = h->batch_users;
+  const int64_t U = h->U;
+  const int64_t n_mb = (U + B - 1) / B;
+  h->plan.clear();
+  std::vector<WorkItem> in, out;
+  std::vector<int32_t> uids;
+  in.reserve((size_t)(U + h->nnz / h->ch_in));
+  out.reserve((size_t)(U + h->nnz / h->ch_out));
+  int64_t max_slots = 0, max_users = 0;
+  for (int64_t mb = 0; mb < n_mb; ++mb) {
+    const int64_t lo = mb * B, n = std::min<int64_t>(B, U - lo);
+    const int64_t a = lo + (n * h->rank) / h->world, b = lo + (n * (h->rank + 1)) / h->world;
+    MiniBatch p;
+    p.user0 = (int64_t)uids.size();
+    p.uid0 = a;
+    p.n_users = b - a;
+    p.in0 = (int64_t)in.size();
+    p.out0 = (int64_t)out.size();
+    int64_t slots = 0;
+    build_items(h->row_ptr_h.data(), nullptr, b - a, a, h->ch_in, h->ch_out, &in, &out, &slots);
+    for (int64_t u = a; u < b; ++u) {
+      if (h->row_ptr_h[u + 1] == h->row_ptr_h[u])
+        return set_error(CDAE_E_INVALID, "user %lld has no train item (reference CHECK, cdae.hpp:139)", (long long)u);
+      uids.push_back((int32_t)u);
+    }
+    p.n_in = (int64_t)in.size() - p.in0;
+    p.n_out = (int64_t)out.size() - p.out0;
+    p.slots = slots;
+    max_slots = std::max(max_slots, slots);
+    max_users = std::max(max_users, p.n_users);
+    h->plan.push_back(p);
+  }
+  TRY(ensure(h, h->plan_in, in.size()));
+  TRY(ensure(h, h->plan_out, out.size()));
+  TRY(ensure(h, h->plan_uids, uids.size()));
+  CU(cudaMemcpyAsync(h->plan_in.p, in.data(), in.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->plan_out.p, out.data(), out.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->plan_uids.p, uids.data(), uids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+  h->plan_max_slots = max_slots;
+  h->plan_max_users = max_users;
+  h->plan_valid = true;
+  return 0;
+}
+
+static int ensure_scratch(cdae_handle* h, int64_t users, int64_t slots) {
+  TRY(ensure(h, h->keep, (size_t)std::max<int64_t>(slots, 1)));
+  TRY(ensure(h, h->negs, (size_t)std::max<int64_t>(slots * std::max(h->cfg.num_neg, 1), 1)));
+  // H | HG | GU are zeroed together each minibatch; Z and D are fully overwritten
+  const size_t per = (size_t)std::max<int64_t>(users, 1) * h->ld;
+  TRY(ensure(h, h->acc3, per * 3));
+  TRY(ensure(h, h->zd, per * 2));
+  h->scratch_users = users;
+  return 0;
+}
+
+static BatchDev make_batch(cdae_handle* h, const WorkItem* in, int64_t n_in, const WorkItem* out,
+                           int64_t n_out, const int32_t* uids, int64_t n_users) {
+  BatchDev bt;
+  const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
+  bt.in_items = in; bt.out_items = out;
+  bt.n_in_items = (int)n_in; bt.n_out_items = (int)n_out; bt.n_users = (int)n_users;
+  bt.uids = uids;
+  bt.row_ptr = h->row_ptr_d.p; bt.col = h->col_d.p;
+  bt.keep = h->keep.p; bt.negs = h->negs.p;
+  bt.H = h->acc3.p; bt.HG = h->acc3.p + per; bt.GU = h->acc3.p + 2 * per;
+  bt.Z = h->zd.p; bt.D = h->zd.p + per;
+  return bt;
+}
+
+// launch one of the <G,NV> row-geometry instantiations by leading dimension
+#define DISPATCH_LD(ld, CALL)                                  \
+  do {                                                         \
+    if ((ld) <= 16) { CALL(4, 1); }                            \
+    else if ((ld) <= 32) { CALL(8, 1); }                       \
+    else if ((ld) <= 64) { CALL(16, 1); }                      \
+    else if ((ld) <= 128) { CALL(32, 1); }                     \
+    else if ((ld) <= 256) { CALL(32, 2); }                     \
+    else if ((ld) <= 384) { CALL(32, 3); }                     \
+    else { CALL(32, 4); }                                      \
+  } while (0)
+
+static int launch_gather(cdae_handle* h, const BatchDev& bt) {
+  if (bt.n_in_items == 0) return 0;
+  ProfScope ps(h, CDAE_K_GATHER);
+  const int grid = cdiv((int64_t)bt.n_in_items * 32, 256);
+#define CALL(G, NV) gather_kernel<G, NV><<<grid, 256, 0, h->stream>>>(h->m, bt)
+  DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  KERNEL_OK(h);
+  return 0;
+}
+static int launch_scatter(cdae_handle* h, const BatchDev& bt) {
+  if (bt.n_in_items == 0) return 0;
+  ProfScope ps(h, CDAE_K_SCATTER);
+  const int grid = cdiv((int64_t)bt.n_in_items * 32, 256);
+#define CALL(G, NV) scatter_kernel<G, NV><<<grid, 256, 0, h->stream>>>(h->m, bt)
+  DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  KERNEL_OK(h);
+  return 0;
+}
+static int launch_decode(cdae_handle* h, const BatchDev& bt, bool train) {
+  if (bt.n_out_items == 0) return 0;
+  ProfScope ps(h, CDAE_K_DECODE);
+  const int grid = cdiv((int64_t)bt.n_out_items * 32, 256);
+  if (train) {
+#define CALL(G, NV) decode_kernel<G, NV, true><<<grid, 256, 0, h->stream>>>(h->m, bt, h->stats_d)
+    DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  } else {
+#define CALL(G, NV) decode_kernel<G, NV, false><<<grid, 256, 0, h->stream>>>(h->m, bt, h->stats_d)
+    DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  }
+  KERNEL_OK(h);
+  return 0;
+}
+static int launch_activate(cdae_handle* h, const BatchDev& bt, float scale) {
+  if (bt.n_users == 0) return 0;
+  ProfScope ps(h, CDAE_K_ACTIVATE);
+  activate_kernel<<<cdiv((int64_t)bt.n_users * (h->ld / 4), 256), 256, 0, h->stream>>>(h->m, bt, scale);
+  KERNEL_OK(h);
+  return 0;
+}
+static int launch_sample(cdae_handle* h, const BatchDev& bt, uint64_t seed, uint32_t pass,
+                         bool need_negs, bool count_kept) {
+  if (bt.n_in_items == 0) return 0;
+  ProfScope ps(h, CDAE_K_SAMPLE);
+  const double q = h->cfg.corruption_ratio;
+  int mode = 2;
+  uint32_t thr = 0;
+  if (q <= 0.) mode = 0;
+  else if (q >= 1.) mode = 1;
+  else thr = (uint32_t)std::floor(q * 4294967296.0);
+  sample_kernel<<<cdiv((int64_t)bt.n_in_items * 32, 256), 256, 0, h->stream>>>(
+      bt, need_negs ? h->cfg.num_neg : 0, h->I, seed, pass, thr, mode, count_kept ? h->stats_d : nullptr);
+  KERNEL_OK(h);
+  return 0;
+}
+
+// gather -> activate -> decode -> hidden_backward -> scatter -> [all-reduce] -> apply
+static int run_train_minibatch(cdae_handle* h, const BatchDev& bt) {
+  const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
+  CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per * (h->m.linear_function ? 3 : 2), h->stream));
+  TRY(launch_gather(h, bt));
+  TRY(launch_activate(h, bt, h->m.scale));
+  TRY(launch_decode(h, bt, true));
+  if (bt.n_users > 0) {
+    ProfScope ps(h, CDAE_K_HIDDEN_BWD);
+    const int bx = h->ld / 4, by = std::max(1, 256 / bx);
+    hidden_backward_kernel<<<cdiv(bt.n_users, by), dim3(bx, by), sizeof(float4) * bx * by, h->stream>>>(h->m, bt, h->stats_d);
+    KERNEL_OK(h);
+  }
+  TRY(launch_scatter(h, bt));
+  if (h->m.linear_function && bt.n_users > 0) {
+    uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt);
+    KERNEL_OK(h);
+  }
+  if (h->world > 1) {
+    ProfScope ps(h, CDAE_K_ALLREDUCE);
+    NC(g_nccl.AllReduce(h->grad.p, h->grad.p, h->grad_floats, kNcclFloat, kNcclSum,
+                        (ncclComm_t)h->comm, h->stream));
+  }
+  ProfScope ps_apply(h, CDAE_K_APPLY);
+  ApplyArgs a;
+  a.nseg = 0;
+  a.lr = h->m.lr; a.beta = h->m.beta; a.adagrad = h->m.adagrad; a.g_steps = h->m.g_steps;
+  a.seg[a.nseg++] = ApplySeg{h->m.W, h->m.W_ag, h->m.gW, h->I * h->ld / 4, 0.f};
+  if (h->m.asym) a.seg[a.nseg++] = ApplySeg{h->m.V, h->m.V_ag, h->m.gV, h->I * h->ld / 4, 0.f};
+  a.seg[a.nseg++] = ApplySeg{h->m.bp, h->m.bp_ag, h->m.gbp, h->I4 / 4, 0.f};
+  a.seg[a.nseg++] = ApplySeg{h->m.b, h->m.b_ag, h->m.gb, h->ld / 4, h->m.lambda};
+  apply_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(a);
+  KERNEL_OK(h);
+  CU(cudaMemsetAsync(h->m.g_steps, 0, sizeof(float) * 4, h->stream));
+  return 0;
+}
+
+static int begin_call(cdae_handle* h) {
+  CU(cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  h->h2d = h->d2h = 0;
+  CU(cudaMemsetAsync(h->stats_d, 0, sizeof(StatsDev), h->stream));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  return 0;
+}
+static int end_call(cdae_handle* h, cdae_epoch_stats_t* stats) {
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaMemcpyAsync(h->stats_h, h->stats_d, sizeof(StatsDev), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->d2h += sizeof(StatsDev);
+  if (h->profiling) h->prof_collect();
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (stats) {
+    stats->user_steps = (int64_t)h->stats_h->user_steps;
+    stats->outputs = (int64_t)h->stats_h->outputs;
+    stats->inputs_kept = (int64_t)h->stats_h->inputs_kept;
+    stats->loss_sum = h->stats_h->loss_sum;
+    stats->device_ms = ms;
+    stats->kernel_launches = h->launches;
+    stats->h2d_bytes = h->h2d;
+    stats->d2h_bytes = h->d2h;
+  }
+  if (h->stats_h->bad_loss)
+    return set_error(CDAE_E_NUMERIC, "LOGISTIC loss received a score outside (0,1) "
+                     "(the reference CHECK-aborts here, loss.hpp:96; use CROSS_ENTROPY)");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int cdae_abi_version(void) { return CDAE_B200_ABI_VERSION; }
+const char* cdae_last_error(void) { return g_last_error.c_str(); }
+
+int cdae_config_default(cdae_config_t* c) {
+  if (!c) return set_error(CDAE_E_INVALID, "cfg is NULL");
+  memset(c, 0, sizeof(*c));
+  c->lambda = 0.01; c->learn_rate = 0.1; c->corruption_ratio = 0.5; c->beta = 0.;
+  c->loss_type = CDAE_LOSS_LOGISTIC; c->num_dim = 10; c->num_neg = 5; c->num_corruptions = 1;
+  c->using_adagrad = 1; c->asymmetric = 0; c->user_factor = 1; c->linear = 0; c->scaled = 1;
+  c->linear_function = 0; c->tanh_act = 0;
+  c->batch_users = 0; c->device = 0;
+  return 0;
+}
+
+int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* row_ptr,
+                const int32_t* col, cdae_handle** out) {
+  if (!cfg || !row_ptr || !out || (!col && row_ptr[U] > 0)) return set_error(CDAE_E_INVALID, "NULL argument");
+  if (U <= 0 || I <= 0 || U > 0x7fffffff || I > 0x7fffffff) return set_error(CDAE_E_INVALID, "need 0 < U, I < 2^31");
+  if (cfg->num_dim < 1 || cfg->num_dim > 512) return set_error(CDAE_E_INVALID, "num_dim must be in [1,512]");
+  if (cfg->num_neg < 0 || cfg->num_corruptions < 1) return set_error(CDAE_E_INVALID, "num_neg >= 0 and num_corruptions >= 1 required");
+  if (cfg->loss_type < 0 || cfg->loss_type > CDAE_LOSS_LOGM) return set_error(CDAE_E_INVALID, "unknown loss_type %d", cfg->loss_type);
+  if (row_ptr[U] >= 0x7fffffff) return set_error(CDAE_E_INVALID, "nnz must be < 2^31");
+  TRY(validate_csr(U, I, row_ptr, col));
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error(CDAE_E_INVALID, "device %d of %d", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+
+  cdae_handle* h = new cdae_handle();
+  h->cfg = *cfg;
+  h->U = U; h->I = I; h->K = cfg->num_dim;
+  h->ld = (int)round_up(cfg->num_dim, 8);
+  h->I4 = round_up(I, 4);
+  h->nnz = row_ptr[U];
+  h->batch_users = cfg->batch_users > 0 ? cfg->batch_users : 8192;
+  h->ch_in = 64;
+  h->ch_out = std::max(1, 96 / (1 + cfg->num_neg));
+  h->rank = 0; h->world = 1;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(cudaMalloc(&h->stats_d, sizeof(StatsDev)));
+  CU(cudaMallocHost(&h->stats_h, sizeof(StatsDev)));
+
+  ModelDev& m = h->m;
+  memset(&m, 0, sizeof(m));
+  m.I = I; m.U = U; m.K = h->K; m.ld = h->ld;
+  m.lambda = (float)cfg->lambda; m.lr = (float)cfg->learn_rate; m.beta = (float)cfg->beta;
+  m.scale = cfg->scaled ? (float)(1. / (1. - cfg->corruption_ratio)) : 1.f;  // cdae.hpp:202-205
+  m.loss = cfg->loss_type; m.nu = cfg->num_neg;
+  m.adagrad = cfg->using_adagrad; m.asym = cfg->asymmetric; m.user_factor = cfg->user_factor;
+  m.linear = cfg->linear; m.tanh_act = cfg->tanh_act; m.linear_function = cfg->linear_function;
+
+  int rc = 0;
+  do {
+    // cdae.hpp:109-134: accumulators 1e-4, b = b' = 0, Uu = 1
+    if ((rc = alloc_table(h, &m.W, I, h->K, h->ld, 0.f))) break;
+    if ((rc = alloc_table(h, &m.W_ag, I, h->K, h->ld, 1e-4f))) break;
+    if (cfg->asymmetric) {
+      if ((rc = alloc_table(h, &m.V, I, h->K, h->ld, 0.f))) break;
+      if ((rc = alloc_table(h, &m.V_ag, I, h->K, h->ld, 1e-4f))) break;
+    }
+    if (cfg->user_factor) {
+      if ((rc = alloc_table(h, &m.Wu, U, h->K, h->ld, 0.f))) break;
+      if ((rc = alloc_table(h, &m.Wu_ag, U, h->K, h->ld, 1e-4f))) break;
+    }
+    if (cfg->linear_function) {
+      if ((rc = alloc_table(h, &m.Uu, U, h->K, h->ld, 1.f))) break;
+      if ((rc = alloc_table(h, &m.Uu_ag, U, h->K, h->ld, 1e-4f))) break;
+    }
+    if ((rc = alloc_table(h, &m.b, 1, h->K, h->ld, 0.f))) break;
+    if ((rc = alloc_table(h, &m.b_ag, 1, h->K, h->ld, 1e-4f))) break;
+    if ((rc = alloc_table(h, &m.bp, 1, (int)I, (int)h->I4, 0.f))) break;
+    if ((rc = alloc_table(h, &m.bp_ag, 1, (int)I, (int)h->I4, 1e-4f))) break;
+    // one contiguous gradient buffer: [gW | gV | gb' | gb | steps]
+    h->grad_floats = (size_t)(I * h->ld) * (cfg->asymmetric ? 2 : 1) + (size_t)h->I4 + (size_t)h->ld + 4;
+    if ((rc = ensure(h, h->grad, h->grad_floats))) break;
+    if (cudaMemsetAsync(h->grad.p, 0, sizeof(float) * h->grad_floats, h->stream) != cudaSuccess) { rc = set_error(CDAE_E_CUDA, "memset"); break; }
+    float* g = h->grad.p;
+    m.gW = g; g += I * h->ld;
+    if (cfg->asymmetric) { m.gV = g; g += I * h->ld; }
+    m.gbp = g; g += h->I4;
+    m.gb = g; g += h->ld;
+    m.g_steps = g;
+    // CSR
+    h->row_ptr_h.assign(row_ptr, row_ptr + U + 1);
+    if ((rc = ensure(h, h->row_ptr_d, (size_t)U + 1))) break;
+    if ((rc = ensure(h, h->col_d, (size_t)std::max<int64_t>(h->nnz, 1)))) break;
+    if (cudaMemcpyAsync(h->row_ptr_d.p, row_ptr, sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+        cudaMemcpyAsync(h->col_d.p, col, sizeof(int32_t) * h->nnz, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      rc = set_error(CDAE_E_CUDA, "CSR upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+  } while (0);
+  if (rc) {
+    cdae_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int cdae_destroy(cdae_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
+  ModelDev& m = h->m;
+  float* tabs[] = {m.W, m.V, m.Wu, m.b, m.bp, m.Uu, m.W_ag, m.V_ag, m.Wu_ag, m.b_ag, m.bp_ag, m.Uu_ag};
+  for (float* p : tabs) if (p) cudaFree(p);
+  h->grad.release(); h->row_ptr_d.release(); h->col_d.release();
+  h->plan_in.release(); h->plan_out.release(); h->plan_uids.release();
+  h->tmp_in.release(); h->tmp_out.release(); h->tmp_uids.release();
+  h->keep.release(); h->negs.release(); h->acc3.release(); h->zd.release();
+  h->stage_d.release(); h->stage_f.release();
+  h->topn_ids.release(); h->topn_scores.release(); h->topn_z.release();
+  h->cand_id.release(); h->cand_cnt.release(); h->cand_s.release(); h->flag_d.release();
+  h->test_rp_d.release(); h->test_col_d.release();
+  if (h->stats_d) cudaFree(h->stats_d);
+  if (h->stats_h) cudaFreeHost(h->stats_h);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int cdae_init_params(cdae_handle* h, uint64_t seed) {
+  if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  CU(cudaSetDevice(h->cfg.device));
+  const double scale = 4. * std::sqrt(6. / (double)(h->I + h->K));
+  struct { float* p; int64_t rows; uint32_t which; } blocks[3] = {
+      {h->m.W, h->I, CDAE_P_W}, {h->m.V, h->I, CDAE_P_V}, {h->m.Wu, h->U, CDAE_P_WU}};
+  for (auto& b : blocks) {
+    if (!b.p) continue;
+    init_uniform_kernel<<<cdiv(b.rows * h->K, 256), 256, 0, h->stream>>>(b.p, b.rows, h->K, h->ld, scale, seed, b.which);
+    KERNEL_OK(h);
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cdae_param_shape(cdae_handle* h, int which, int64_t* rows, int64_t* cols) {
+  if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  int64_t r, c; int ld;
+  if (!param_ptr(h, which, &r, &c, &ld) && (which < 0 || which >= CDAE_P_COUNT))
+    return set_error(CDAE_E_INVALID, "unknown parameter block %d", which);
+  // report vectors the way the reference declares them: b is K x 1, b' is I x 1
+  if (which == CDAE_P_B || which == CDAE_P_B_AG || which == CDAE_P_BPRIME || which == CDAE_P_BPRIME_AG) { r = c; c = 1; }
+  if (rows) *rows = r;
+  if (cols) *cols = c;
+  return 0;
+}
+
+int cdae_set_param(cdae_handle* h, int which, const double* src, int64_t n) {
+  if (!h || (!src && n > 0)) return set_error(CDAE_E_INVALID, "NULL argument");
+  CU(cudaSetDevice(h->cfg.device));
+  int64_t r, c; int ld;
+  float* p = param_ptr(h, which, &r, &c, &ld);
+  if (which < 0 || which >= CDAE_P_COUNT) return set_error(CDAE_E_INVALID, "unknown parameter block %d", which);
+  if (n != r * c) return set_error(CDAE_E_INVALID, "block %d holds %lld values, got %lld", which, (long long)(r * c), (long long)n);
+  if (n == 0) return 0;
+  const bool vec_bp = which == CDAE_P_BPRIME || which == CDAE_P_BPRIME_AG;
+  TRY(ensure(h, h->stage_d, (size_t)n));
+  CU(cudaMemcpyAsync(h->stage_d.p, src, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  const int K = (int)c, L = vec_bp ? (int)c : ld;
+  pack_from_double_kernel<<<cdiv(r * L, 256), 256, 0, h->stream>>>(p, h->stage_d.p, r, K, L);
+  KERNEL_OK(h);
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cdae_get_param(cdae_handle* h, int which, double* dst, int64_t n) {
+  if (!h || (!dst && n > 0)) return set_error(CDAE_E_INVALID, "NULL argument");
+  CU(cudaSetDevice(h->cfg.device));
+  int64_t r, c; int ld;
+  float* p = param_ptr(h, which, &r, &c, &ld);
+  if (which < 0 || which >= CDAE_P_COUNT) return set_error(CDAE_E_INVALID, "unknown parameter block %d", which);
+  if (n != r * c) return set_error(CDAE_E_INVALID, "block %d holds %lld values, got %lld", which, (long long)(r * c), (long long)n);
+  if (n == 0) return 0;
+  const bool vec_bp = which == CDAE_P_BPRIME || which == CDAE_P_BPRIME_AG;
+  const bool user_block = which == CDAE_P_WU || which == CDAE_P_WU_AG || which == CDAE_P_UU || which == CDAE_P_UU_AG;
+  TRY(ensure(h, h->stage_d, (size_t)n));
+  const int K = (int)c, L = vec_bp ? (int)c : ld;
+  const float* src = p;
+  if (h->world > 1 && user_block) {
+    // user rows are only ever updated by their owning rank: keep owned rows, zero the rest,
+    // and sum across ranks (rows nobody trained are identical everywhere -> divide is avoided
+    // by letting rank ownership cover every row exactly once).
+    TRY(ensure(h, h->stage_f, (size_t)(r * ld)));
+    owned_rows_kernel<<<cdiv(r * ld, 256), 256, 0, h->stream>>>(h->stage_f.p, p, r, ld, h->batch_users, h->U, h->rank, h->world);
+    KERNEL_OK(h);
+    NC(g_nccl.AllReduce(h->stage_f.p, h->stage_f.p, (size_t)(r * ld), kNcclFloat, kNcclSum, (ncclComm_t)h->comm, h->stream));
+    src = h->stage_f.p;
+  }
+  unpack_to_double_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->stage_d.p, src, r, K, L);
+  KERNEL_OK(h);
+  CU(cudaMemcpyAsync(dst, h->stage_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats) {
+  if (!h->plan_valid) TRY(build_plan(h));
+  TRY(ensure_scratch(h, h->plan_max_users, h->plan_max_slots));
+  const int cnum = h->cfg.num_corruptions;
+  for (const MiniBatch& p : h->plan) {
+    for (int c = 0; c < cnum; ++c) {
+      BatchDev bt = make_batch(h, h->plan_in.p + p.in0, p.n_in, h->plan_out.p + p.out0, p.n_out,
+                               h->plan_uids.p + p.user0, p.n_users);
+      TRY(launch_sample(h, bt, seed, (uint32_t)(epoch * cnum + c), true, true));
+      TRY(run_train_minibatch(h, bt));
+    }
+  }
+  return end_call(h, stats);
+}
+
+int cdae_train_epoch(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats) {
+  if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  TRY(begin_call(h));
+  return train_epoch_impl(h, seed, epoch, stats);
+}
+
+int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* col, uint64_t seed,
+                         int64_t epoch, cdae_epoch_stats_t* stats) {
+  if (!h || !row_ptr || !col) return set_error(CDAE_E_INVALID, "NULL argument");
+  TRY(begin_call(h));
+  const int64_t nnz = row_ptr[h->U];
+  if (nnz >= 0x7fffffff) return set_error(CDAE_E_INVALID, "nnz must be < 2^31");
+  // the work lists depend on row_ptr only: rebuild them only when the row structure changed
+  const bool same_rows = nnz == h->nnz && memcmp(row_ptr, h->row_ptr_h.data(), sizeof(int64_t) * (h->U + 1)) == 0;
+  if (!same_rows) {
+    h->row_ptr_h.assign(row_ptr, row_ptr + h->U + 1);
+    h->nnz = nnz;
+    h->plan_valid = false;
+    TRY(ensure(h, h->col_d, (size_t)std::max<int64_t>(nnz, 1)));
+  }
+  CU(cudaMemcpyAsync(h->row_ptr_d.p, row_ptr, sizeof(int64_t) * (h->U + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->col_d.p, col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
+  h->h2d += sizeof(int64_t) * (h->U + 1) + sizeof(int32_t) * nnz;
+  return train_epoch_impl(h, seed, epoch, stats);
+}
+
+// Upload the work lists of an explicit user list into the tmp_* buffers.
+static int stage_users(cdae_handle* h, const int64_t* uids, int64_t n, bool want_out, int64_t* slots,
+                       int64_t* n_in, int64_t* n_out) {
+  std::vector<WorkItem> in, out;
+  std::vector<int32_t> u32((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (uids[i] < 0 || uids[i] >= h->U) return set_error(CDAE_E_INVALID, "uid %lld outside [0,%lld)", (long long)uids[i], (long long)h->U);
+    u32[(size_t)i] = (int32_t)uids[i];
+  }
+  build_items(h->row_ptr_h.data(), uids, n, 0, h->ch_in, h->ch_out, &in, want_out ? &out : nullptr, slots);
+  TRY(ensure(h, h->tmp_in, std::max<size_t>(in.size(), 1)));
+  TRY(ensure(h, h->tmp_out, std::max<size_t>(out.size(), 1)));
+  TRY(ensure(h, h->tmp_uids, std::max<size_t>(u32.size(), 1)));
+  if (!in.empty()) CU(cudaMemcpyAsync(h->tmp_in.p, in.data(), in.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, h->stream));
+  if (!out.empty()) CU(cudaMemcpyAsync(h->tmp_out.p, out.data(), out.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, h->stream));
+  if (n) CU(cudaMemcpyAsync(h->tmp_uids.p, u32.data(), u32.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *n_in = (int64_t)in.size();
+  *n_out = (int64_t)out.size();
+  return 0;
+}
+
+int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* keep_mask,
+                     const int32_t* negatives, cdae_epoch_stats_t* stats) {
+  if (!h || !uids || n <= 0) return set_error(CDAE_E_INVALID, "need a non-empty uid list");
+  if (h->world > 1) return set_error(CDAE_E_STATE, "cdae_train_users is single-process (explicit inputs)");
+  TRY(begin_call(h));
+  int64_t slots = 0, n_in = 0, n_out = 0;
+  TRY(stage_users(h, uids, n, true, &slots, &n_in, &n_out));
+  if (slots > 0 && !keep_mask) return set_error(CDAE_E_INVALID, "keep_mask is NULL");
+  if (slots * h->cfg.num_neg > 0 && !negatives) return set_error(CDAE_E_INVALID, "negatives is NULL");
+  {  // distinct users, non-empty rows, negatives outside the user's row
+    std::vector<int64_t> s(uids, uids + n);
+    std::sort(s.begin(), s.end());
+    if (std::adjacent_find(s.begin(), s.end()) != s.end()) return set_error(CDAE_E_INVALID, "uids must be distinct inside one frozen minibatch");
+    int64_t off = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t nu_ = h->row_ptr_h[uids[i] + 1] - h->row_ptr_h[uids[i]];
+      if (nu_ == 0) return set_error(CDAE_E_INVALID, "user %lld has no train item (reference CHECK, cdae.hpp:139)", (long long)uids[i]);
+      for (int64_t j = 0; j < nu_ * h->cfg.num_neg; ++j)
+        if (negatives[off * h->cfg.num_neg + j] < 0 || negatives[off * h->cfg.num_neg + j] >= h->I)
+          return set_error(CDAE_E_INVALID, "negative id out of range");
+      off += nu_;
+    }
+  }
+  TRY(ensure_scratch(h, n, slots));
+  CU(cudaMemcpyAsync(h->keep.p, keep_mask, (size_t)slots, cudaMemcpyHostToDevice, h->stream));
+  if (slots * h->cfg.num_neg > 0)
+    CU(cudaMemcpyAsync(h->negs.p, negatives, sizeof(int32_t) * (size_t)(slots * h->cfg.num_neg), cudaMemcpyHostToDevice, h->stream));
+  h->h2d += (size_t)slots + sizeof(int32_t) * (size_t)(slots * h->cfg.num_neg);
+  BatchDev bt = make_batch(h, h->tmp_in.p, n_in, h->tmp_out.p, n_out, h->tmp_uids.p, n);
+  TRY(run_train_minibatch(h, bt));
+  return end_call(h, stats);
+}
+
+int cdae_encode(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* keep_mask, double scale,
+                float* z_out) {
+  if (!h || !uids || !z_out || n <= 0) return set_error(CDAE_E_INVALID, "NULL / empty argument");
+  TRY(begin_call(h));
+  int64_t slots = 0, n_in = 0, n_out = 0;
+  TRY(stage_users(h, uids, n, false, &slots, &n_in, &n_out));
+  TRY(ensure_scratch(h, n, slots));
+  if (keep_mask) {
+    CU(cudaMemcpyAsync(h->keep.p, keep_mask, (size_t)slots, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CU(cudaMemsetAsync(h->keep.p, 1, (size_t)std::max<int64_t>(slots, 1), h->stream));
+  }
+  BatchDev bt = make_batch(h, h->tmp_in.p, n_in, h->tmp_out.p, 0, h->tmp_uids.p, n);
+  const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
+  CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per, h->stream));
+  TRY(launch_gather(h, bt));
+  TRY(launch_activate(h, bt, (float)scale));
+  TRY(ensure(h, h->stage_f, (size_t)(n * h->K)));
+  unpack_to_float_kernel<<<cdiv(n * h->K, 256), 256, 0, h->stream>>>(h->stage_f.p, bt.Z, n, h->K, h->ld);
+  KERNEL_OK(h);
+  CU(cudaMemcpyAsync(z_out, h->stage_f.p, sizeof(float) * n * h->K, cudaMemcpyDeviceToHost, h->stream));
+  h->d2h += sizeof(float) * n * h->K;
+  return end_call(h, nullptr);
+}
+
+int cdae_data_loss(cdae_handle* h, uint64_t seed, double* out) {
+  if (!h || !out) return set_error(CDAE_E_INVALID, "NULL argument");
+  TRY(begin_call(h));
+  if (!h->plan_valid) TRY(build_plan(h));
+  TRY(ensure_scratch(h, h->plan_max_users, h->plan_max_slots));
+  const int cnum = h->cfg.num_corruptions;
+  const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
+  for (const MiniBatch& p : h->plan) {
+    for (int c = 0; c < cnum; ++c) {
+      BatchDev bt = make_batch(h, h->plan_in.p + p.in0, p.n_in, h->plan_out.p + p.out0, p.n_out,
+                               h->plan_uids.p + p.user0, p.n_users);
+      TRY(launch_sample(h, bt, seed, 0x80000000u + (uint32_t)c, false, false));
+      CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per, h->stream));
+      TRY(launch_gather(h, bt));
+      TRY(launch_activate(h, bt, h->m.scale));
+      TRY(launch_decode(h, bt, false));
+    }
+  }
+  cdae_epoch_stats_t st;
+  TRY(end_call(h, &st));
+  double v = st.loss_sum / (double)cnum;  // user_rets / num_corruptions_, cdae.hpp:98
+  if (h->world > 1) {
+    // sum of the per-rank partial losses (tiny): reuse the stats staging as a 2-float all-reduce
+    // (hi/lo split keeps double-ish precision)
+    float hl[2] = {(float)v, (float)(v - (double)(float)v)};
+    TRY(ensure(h, h->stage_f, 2));
+    CU(cudaMemcpyAsync(h->stage_f.p, hl, sizeof(hl), cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllReduce(h->stage_f.p, h->stage_f.p, 2, kNcclFloat, kNcclSum, (ncclComm_t)h->comm, h->stream));
+    CU(cudaMemcpyAsync(hl, h->stage_f.p, sizeof(hl), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    v = (double)hl[0] + (double)hl[1];
+  }
+  *out = v;
+  return 0;
+}
+
+int cdae_penalty_loss(cdae_handle* h, double* out) {
+  if (!h || !out) return set_error(CDAE_E_INVALID, "NULL argument");
+  CU(cudaSetDevice(h->cfg.device));
+  TRY(ensure(h, h->stage_d, 1));
+  CU(cudaMemsetAsync(h->stage_d.p, 0, sizeof(double), h->stream));
+  struct { const float* p; int64_t n; } blocks[5] = {
+      {h->m.W, h->I * h->ld}, {h->m.V, h->m.V ? h->I * h->ld : 0}, {h->m.Wu, h->m.Wu ? h->U * h->ld : 0},
+      {h->m.b, h->ld}, {h->m.bp, h->I4}};
+  if (h->world > 1 && h->m.Wu) return set_error(CDAE_E_STATE, "penalty_loss with user_factor in a process group: fetch Wu with cdae_get_param instead");
+  for (auto& b : blocks) {
+    if (!b.p || b.n == 0) continue;  // pad entries are exactly 0 and do not contribute
+    sumsq_kernel<<<std::min(cdiv(b.n, 256), h->sm_count * 8), 256, 0, h->stream>>>(b.p, b.n, h->stage_d.p);
+    KERNEL_OK(h);
+  }
+  double s = 0.;
+  CU(cudaMemcpyAsync(&s, h->stage_d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *out = 0.5 * h->cfg.lambda * s;  // cdae.hpp:104
+  return 0;
+}
+
+int cdae_dist_unique_id(void* id128_out) {
+  if (!id128_out) return set_error(CDAE_E_INVALID, "NULL argument");
+  TRY(load_nccl());
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(id128_out, &id, sizeof(id));
+  return 0;
+}
+
+int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id) {
+  if (!h || !nccl_unique_id || world < 1 || rank < 0 || rank >= world) return set_error(CDAE_E_INVALID, "bad rank/world");
+  if (h->comm) return set_error(CDAE_E_STATE, "process group already initialised");
+  TRY(load_nccl());
+  CU(cudaSetDevice(h->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NC(g_nccl.CommInitRank(&comm, world, id, rank));
+  h->comm = comm;
+  h->rank = rank; h->world = world;
+  h->plan_valid = false;
+  return 0;
+}
+
+int cdae_profile(cdae_handle* h, int32_t enable) {
+  if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  h->profiling = enable != 0;
+  for (int c = 0; c < CDAE_K_COUNT; ++c) { h->prof_ms[c] = 0.; h->prof_n[c] = 0; }
+  h->prof_used = 0;
+  return 0;
+}
+int cdae_profile_get(cdae_handle* h, double* ms_out, int64_t* launches_out) {
+  if (!h || !ms_out || !launches_out) return set_error(CDAE_E_INVALID, "NULL argument");
+  for (int c = 0; c < CDAE_K_COUNT; ++c) { ms_out[c] = h->prof_ms[c]; launches_out[c] = h->prof_n[c]; }
+  return 0;
+}
+
+int cdae_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return set_error(CDAE_E_INVALID, "bad argument");
+  CU(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return 0;
+}
+int cdae_host_free(void* ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
+  return 0;
+}
+int cdae_synchronize(cdae_handle* h) {
+  if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int cdae_stream(cdae_handle* h, void** stream_out) {
+  if (!h || !stream_out) return set_error(CDAE_E_INVALID, "NULL argument");
+  *stream_out = (void*)h->stream;
+  return 0;
+}
+
+}  // extern "C"
+
+// Phase A of recommend: per-user candidate lists (TOPN_M best by score).
+static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users) {
+  const size_t dyn = (size_t)TT_U * TOPN_M * (sizeof(float) + sizeof(int));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(topn_tile_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  ProfScope ps(h, CDAE_K_TOPN);
+  topn_tile_fp32_kernel<<<cdiv(n_users, TT_U), 256, dyn, h->stream>>>(
+      h->topn_z.p, Wd, h->m.bp, h->I, h->ld, users, (int)n_users, h->row_ptr_d.p, h->col_d.p,
+      h->cand_id.p, h->cand_s.p, h->cand_cnt.p);
+  KERNEL_OK(h);
+  return 0;
+}
+
+#include "topn_api.inl"

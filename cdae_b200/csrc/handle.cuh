@@ -1,0 +1,127 @@
+// cdae_b200/csrc/handle.cuh — the state behind an opaque cdae_handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/cdae_b200.h"
+#include "train_kernels.cuh"
+
+namespace cdae {
+
+int set_error(int code, const char* fmt, ...);
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// This rank's slice of one global minibatch, as ranges into the plan_* lists.
+struct MiniBatch {
+  int64_t user0, n_users;  // range in plan_uids
+  int64_t uid0;            // first global uid of the slice (slices are contiguous)
+  int64_t in0, n_in;       // range in plan_in
+  int64_t out0, n_out;     // range in plan_out
+  int64_t slots;           // train items of the slice (size of keep[], negs[] / num_neg)
+};
+
+}  // namespace cdae
+
+struct cdae_handle {
+  cdae_config_t cfg;
+  int64_t U = 0, I = 0, I4 = 0, nnz = 0;
+  int K = 0, ld = 0;
+  int64_t batch_users = 0;
+  int ch_in = 64, ch_out = 16;
+  int rank = 0, world = 1;
+  void* comm = nullptr;  // ncclComm_t
+  int sm_count = 148;
+  size_t dev_bytes = 0;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cdae::ModelDev m;
+  cdae::DevBuf<float> grad;
+  size_t grad_floats = 0;
+
+  std::vector<int64_t> row_ptr_h;  // host copy (work lists depend on it)
+  cdae::DevBuf<int64_t> row_ptr_d;
+  cdae::DevBuf<int32_t> col_d;
+
+  // epoch plan
+  std::vector<cdae::MiniBatch> plan;
+  cdae::DevBuf<cdae::WorkItem> plan_in, plan_out;
+  cdae::DevBuf<int32_t> plan_uids;
+  int64_t plan_max_slots = 0, plan_max_users = 0;
+  bool plan_valid = false;
+  // explicit-user calls
+  cdae::DevBuf<cdae::WorkItem> tmp_in, tmp_out;
+  cdae::DevBuf<int32_t> tmp_uids;
+
+  // per-minibatch scratch
+  cdae::DevBuf<uint8_t> keep;
+  cdae::DevBuf<int32_t> negs;
+  cdae::DevBuf<float> acc3;  // H | HG | GU
+  cdae::DevBuf<float> zd;    // Z | D
+  int64_t scratch_users = 0;
+
+  cdae::DevBuf<double> stage_d;
+  cdae::DevBuf<float> stage_f;
+
+  cdae::StatsDev* stats_d = nullptr;
+  cdae::StatsDev* stats_h = nullptr;  // pinned
+  int64_t launches = 0, h2d = 0, d2h = 0;
+
+  // top-N table (cdae_topn_build)
+  cdae::DevBuf<int32_t> topn_ids;     // [U][topk]
+  cdae::DevBuf<float> topn_scores;    // [U][topk]
+  cdae::DevBuf<float> topn_z;         // [U][ld] uncorrupted hidden vectors
+  cdae::DevBuf<int> cand_id, cand_cnt, flag_d;
+  cdae::DevBuf<float> cand_s;
+  cdae::DevBuf<int64_t> test_rp_d;
+  cdae::DevBuf<int32_t> test_col_d;
+  std::vector<int32_t> topn_ids_h;    // host mirror for thread-safe lookups
+  std::vector<float> topn_scores_h;
+  int topn_k = 0;
+
+  // cdae_profile: event pairs per launch, grouped by kernel class
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cls;
+  size_t prof_used = 0;
+  double prof_ms[CDAE_K_COUNT] = {0};
+  int64_t prof_n[CDAE_K_COUNT] = {0};
+  void prof_begin(int cls) {
+    if (prof_used + 2 > prof_ev.size()) {
+      for (int i = 0; i < 64; ++i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        prof_ev.push_back(e);
+      }
+      prof_cls.resize(prof_ev.size() / 2);
+    }
+    prof_cls[prof_used / 2] = cls;
+    cudaEventRecord(prof_ev[prof_used], stream);
+  }
+  void prof_end() {
+    cudaEventRecord(prof_ev[prof_used + 1], stream);
+    prof_used += 2;
+  }
+  void prof_collect() {  // after a stream synchronise
+    for (size_t i = 0; i + 1 < prof_used + 1 && i + 1 < prof_ev.size() && i < prof_used; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]) == cudaSuccess) {
+        prof_ms[prof_cls[i / 2]] += ms;
+        prof_n[prof_cls[i / 2]] += 1;
+      }
+    }
+    prof_used = 0;
+  }
+};

@@ -1,0 +1,570 @@
+// cdae_b200/csrc/train_kernels.cuh — the per-user CDAE step as sm_100a kernels.
+//
+// One frozen minibatch of users (SURVEY.md Appendix A "frozen-batch") runs as
+//   sample  -> gather -> activate -> decode -> hidden_backward -> scatter -> apply
+// All item-side tables are row-major [rows][ld] fp32 with ld = round_up(K, 8) (32-byte
+// sectors; pad columns are kept at exactly 0).  A table row is owned by a GROUP of G lanes,
+// each holding NV float4 (column 4*(v*G+lane) .. +3): loads are 16 B per lane and contiguous
+// across the group, the K-reduction is a log2(G)-step shuffle, and a warp works on 32/G rows
+// at once, unrolled UNR deep so that >= 8 independent row loads are in flight per warp.
+//
+// Reference lines each kernel takes over are cited at the kernel.
+#pragma once
+#include "common.cuh"
+
+namespace cdae {
+
+struct ModelDev {
+  // parameters and AdaGrad state (cdae.hpp:430-439), fp32, leading dimension ld
+  float *W, *V, *Wu, *b, *bp, *Uu;
+  float *W_ag, *V_ag, *Wu_ag, *b_ag, *bp_ag, *Uu_ag;
+  // dense gradient accumulators of one minibatch (one contiguous buffer, all-reduced as one)
+  float *gW, *gV, *gbp, *gb;
+  float* g_steps;  // [1] number of user steps that contributed (for the n*lambda*b term)
+  int64_t I, U;
+  int K, ld;
+  float lambda, lr, beta, scale;  // scale = scaled ? 1/(1-q) : 1   (cdae.hpp:202-205)
+  int loss, nu;
+  int adagrad, asym, user_factor, linear, tanh_act, linear_function;
+};
+
+struct BatchDev {
+  const WorkItem* in_items;   // input chunks  (<= CH_IN slots each)
+  const WorkItem* out_items;  // output chunks (<= ch_out slots each)
+  int n_in_items, n_out_items, n_users;
+  const int32_t* uids;        // [n_users] global uid per local row
+  const int64_t* row_ptr;     // CSR of the training set (device)
+  const int32_t* col;
+  uint8_t* keep;              // [minibatch slots]       1 = input item survives corruption
+  int32_t* negs;              // [minibatch slots * nu]  sampled negatives
+  float *H, *Z, *HG, *D, *GU;  // [n_users][ld]
+};
+
+struct StatsDev {
+  double loss_sum;
+  unsigned long long outputs, inputs_kept, user_steps;
+  int bad_loss;  // LOGISTIC fed a score outside (0,1)
+  int pad;
+};
+
+template <int G, int NV>
+struct RowMap {
+  static constexpr int NG = 32 / G;  // rows a warp handles at once
+  __device__ static __forceinline__ int col4(int gl, int v) { return (v * G + gl) * 4; }
+};
+
+template <int G>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+  return x;
+}
+// sum a per-group partial vector over the 32/G groups of the warp (result valid in all lanes)
+template <int G>
+__device__ __forceinline__ float4 cross_group_sum(float4 a) {
+#pragma unroll
+  for (int off = G; off < 32; off <<= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+    a.z += __shfl_xor_sync(0xffffffffu, a.z, off);
+    a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+  }
+  return a;
+}
+
+__device__ __forceinline__ WorkItem load_item(const WorkItem* p) {
+  WorkItem w;
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  w.uid = a.x; w.u_local = a.y; w.n = a.z; w.aux0 = a.w;
+  w.s0 = (int64_t)(((uint64_t)(uint32_t)b.y << 32) | (uint32_t)b.x);
+  w.first = b.z; w.row_off = b.w;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// H3 + H5: corruption mask (cdae.hpp:361-371: keep iff uniform > q) and negative sampling
+// (recsys_model_base.hpp:46-57: uniform item, redraw while it is one of the user's positives;
+// n_u*num_neg draws with replacement, cdae.hpp:217-220).  One warp per input chunk.
+__global__ void __launch_bounds__(256) sample_kernel(BatchDev bt, int nu, int64_t I, uint64_t seed,
+                                                     uint32_t pass, uint32_t keep_thr,
+                                                     int keep_mode /*0 all,1 none,2 philox*/,
+                                                     StatsDev* stats) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= bt.n_in_items) return;
+  const int lane = threadIdx.x & 31;
+  const WorkItem wi = load_item(bt.in_items + warp);
+  const int64_t r0 = __ldg(bt.row_ptr + wi.uid);
+  const int n_u = (int)(__ldg(bt.row_ptr + wi.uid + 1) - r0);
+  const int32_t* row = bt.col + r0;
+  int kept = 0;
+  for (int i = lane; i < wi.n; i += 32) {
+    const int s = wi.row_off + i;  // position inside the user's row
+    uint8_t k;
+    if (keep_mode == 0) k = 1;
+    else if (keep_mode == 1) k = 0;
+    else {
+      const Philox4 p = philox4x32(seed, (uint32_t)wi.uid, (uint32_t)(s >> 2), pass, 0u);
+      k = philox_word(p, s & 3) > keep_thr;
+    }
+    bt.keep[wi.aux0 + i] = k;
+    kept += k;
+  }
+  const int ndraw = wi.n * nu;
+  int32_t* out = bt.negs + (int64_t)wi.aux0 * nu;
+  for (int j = lane; j < ndraw; j += 32) {
+    const uint32_t d = (uint32_t)(wi.row_off * nu + j);  // draw index inside the user
+    int32_t item = 0;
+    for (uint32_t a = 0;; ++a) {
+      const Philox4 p = philox4x32(seed, (uint32_t)wi.uid, d, pass, 1u + (a >> 2));
+      item = (int32_t)(((uint64_t)philox_word(p, a & 3) * (uint64_t)I) >> 32);
+      int lo = 0, hi = n_u;  // binary search in the user's ascending row
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(row + mid) < item) lo = mid + 1; else hi = mid;
+      }
+      if (!(lo < n_u && __ldg(row + lo) == item)) break;
+    }
+    out[j] = item;
+  }
+  kept = (int)group_sum<32>((float)kept);
+  if (lane == 0 && stats) atomicAdd(&stats->inputs_kept, (unsigned long long)kept);
+}
+
+// ---------------------------------------------------------------------------------------
+// H4 first half, cdae.hpp:375-380: H[u] += sum over kept inputs of W[item]  (the scale factor
+// is applied in activate_kernel).  One warp per input chunk; chunks of one user add up with
+// 16-byte reductions (H is zeroed per minibatch).
+template <int G, int NV>
+__global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt) {
+  using RM = RowMap<G, NV>;
+  constexpr int NG = RM::NG, UNR = 4;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= bt.n_in_items) return;
+  const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+  const WorkItem wi = load_item(bt.in_items + warp);
+  const int32_t* items = bt.col + wi.s0;
+  const uint8_t* keep = bt.keep + wi.aux0;
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+  for (int base = 0; base < wi.n; base += NG * UNR) {
+    int it[UNR];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      const int r = base + t * NG + grp;
+      it[t] = (r < wi.n && keep[r]) ? __ldg(items + r) : -1;
+    }
+    float4 w[UNR][NV];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = RM::col4(gl, v);
+        w[t][v] = (it[t] >= 0 && c < m.ld) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+      }
+#pragma unroll
+    for (int t = 0; t < UNR; ++t)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = add4(acc[v], w[t][v]);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    acc[v] = cross_group_sum<G>(acc[v]);
+    const int c = RM::col4(gl, v);
+    if (grp == 0 && c < m.ld) red_add_v4(bt.H + (int64_t)wi.u_local * m.ld + c, acc[v]);
+  }
+}
+
+// H4 second half, cdae.hpp:382-414: z = act([Uu (.)] scale*H + b [+ Wu[u]]); pad columns -> 0.
+__global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, float scale) {
+  const int ld4n = m.ld / 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)bt.n_users * ld4n) return;
+  const int u = (int)(idx / ld4n), c = (int)(idx % ld4n) * 4;
+  const int64_t uid = bt.uids[u];
+  float4 h = scale4(scale, ld4(bt.H + (int64_t)u * m.ld + c));
+  if (m.linear_function) h = mul4(ld4(m.Uu + uid * m.ld + c), h);
+  h = add4(h, ld4(m.b + c));
+  if (m.user_factor) h = add4(h, ld4(m.Wu + uid * m.ld + c));
+  float x[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!m.linear) x[i] = m.tanh_act ? act_tanh(x[i]) : act_sigmoid(x[i]);
+    if (c + i >= m.K) x[i] = 0.f;
+  }
+  st4(bt.Z + (int64_t)u * m.ld + c, make_float4(x[0], x[1], x[2], x[3]));
+}
+
+// ---------------------------------------------------------------------------------------
+// H6 + H7, cdae.hpp:225-293 (+ get_output_values :418-426, Loss::gradient): for every output
+// o of the chunk (its positives, then their negatives): y = W'[o].z + b'[o]; g = l'(y,t);
+// hg += g*W'[o]; gW'[o] += g*z + lambda*W'[o]; gb'[o] += g + lambda*b'[o].
+// Tied weights and o in the corrupted input: the lambda term is left to scatter_kernel so the
+// row receives ONE lambda per merged occurrence (cdae.hpp:249-250, 342-343).
+// TRAIN=false scores the positives only and accumulates loss(y,1): CDAE::data_loss :93-96.
+template <int G, int NV, bool TRAIN>
+__global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, StatsDev* stats) {
+  using RM = RowMap<G, NV>;
+  constexpr int NG = RM::NG, UNR = 4;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= bt.n_out_items) return;
+  const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+  const WorkItem wi = load_item(bt.out_items + warp);
+  const int32_t* pos = bt.col + wi.s0;
+  const uint8_t* keep = bt.keep + wi.aux0;
+  const int32_t* neg = bt.negs + (int64_t)wi.aux0 * m.nu;
+  const float* Wd = m.asym ? m.V : m.W;
+  float* gWd = m.asym ? m.gV : m.gW;
+  const int n = wi.n;
+  const int R = TRAIN ? n * (1 + m.nu) : n;
+  const bool tied = !m.asym;
+
+  float4 z[NV], hg[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = RM::col4(gl, v);
+    z[v] = c < m.ld ? ld4(bt.Z + (int64_t)wi.u_local * m.ld + c) : f4zero();
+    hg[v] = f4zero();
+  }
+  float loss_acc = 0.f;
+  int bad = 0;
+
+  for (int base = 0; base < R; base += NG * UNR) {
+    int it[UNR];
+    bool merged[UNR];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      const int r = base + t * NG + grp;
+      it[t] = -1;
+      merged[t] = false;
+      if (r < n) {
+        it[t] = __ldg(pos + r);
+        merged[t] = TRAIN && tied && keep[r];
+      } else if (r < R) {
+        it[t] = __ldg(neg + (r - n));
+      }
+    }
+    float4 w[UNR][NV];
+    float bp[UNR];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = RM::col4(gl, v);
+        w[t][v] = (it[t] >= 0 && c < m.ld) ? ld4(Wd + (int64_t)it[t] * m.ld + c) : f4zero();
+      }
+      bp[t] = it[t] >= 0 ? __ldg(m.bp + it[t]) : 0.f;
+    }
+    float y[UNR];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      float p = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) p += dot4(w[t][v], z[v]);
+      y[t] = p;
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int t = 0; t < UNR; ++t) y[t] += __shfl_xor_sync(0xffffffffu, y[t], off);
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      if (it[t] < 0) continue;  // uniform inside the group
+      const int r = base + t * NG + grp;
+      const float truth = r < n ? 1.f : 0.f;
+      float l;
+      const float g = loss_grad(m.loss, y[t] + bp[t], truth, &l, &bad);
+      if (gl == 0) loss_acc += l;
+      if (!TRAIN) continue;
+      const float lam = merged[t] ? 0.f : m.lambda;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = RM::col4(gl, v);
+        hg[v] = fma4(g, w[t][v], hg[v]);
+        if (c < m.ld) red_add_v4(gWd + (int64_t)it[t] * m.ld + c, fma4(g, z[v], scale4(lam, w[t][v])));
+      }
+      if (gl == 0) red_add_f32(m.gbp + it[t], g + m.lambda * bp[t]);
+    }
+  }
+  if (TRAIN) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      hg[v] = cross_group_sum<G>(hg[v]);
+      const int c = RM::col4(gl, v);
+      if (grp == 0 && c < m.ld) red_add_v4(bt.HG + (int64_t)wi.u_local * m.ld + c, hg[v]);
+    }
+  }
+  loss_acc = group_sum<32>(loss_acc);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    atomicAdd(&stats->loss_sum, (double)loss_acc);
+    atomicAdd(&stats->outputs, (unsigned long long)R);
+    if (bad) stats->bad_loss = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// H8 user-local part, cdae.hpp:295-331: delta = hg (.) act'(z) (:208-215); the user's Wu row
+// takes upd(delta + lambda*Wu[u]) in place (rows are user-private, so frozen-batch == online);
+// gb += delta (the n*lambda*b term is added in apply_kernel).  Block = 32 users x ld/4 lanes.
+__global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchDev bt, StatsDev* stats) {
+  extern __shared__ float4 red[];  // [blockDim.y][ld/4]
+  const int ld4n = m.ld / 4;
+  const int c4 = threadIdx.x;  // < ld4n
+  const int u = blockIdx.x * blockDim.y + threadIdx.y;
+  float4 d = f4zero();
+  if (u < bt.n_users && c4 < ld4n) {
+    const int c = c4 * 4;
+    const float4 zz = ld4(bt.Z + (int64_t)u * m.ld + c);
+    const float4 hg = ld4(bt.HG + (int64_t)u * m.ld + c);
+    float4 dz = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (!m.linear) {
+      if (!m.tanh_act) dz = make_float4(zz.x - zz.x * zz.x, zz.y - zz.y * zz.y, zz.z - zz.z * zz.z, zz.w - zz.w * zz.w);
+      else dz = make_float4(1.f - zz.x * zz.x, 1.f - zz.y * zz.y, 1.f - zz.z * zz.z, 1.f - zz.w * zz.w);
+    }
+    d = mul4(hg, dz);
+    // pad columns: hg is exactly 0 there (W' pad columns are 0), so d is 0
+    st4(bt.D + (int64_t)u * m.ld + c, d);
+    if (m.user_factor) {
+      const int64_t uid = bt.uids[u];
+      float* wp = m.Wu + uid * m.ld + c;
+      float* ap = m.Wu_ag + uid * m.ld + c;
+      float4 wv = ld4(wp);
+      float g[4] = {d.x + m.lambda * wv.x, d.y + m.lambda * wv.y, d.z + m.lambda * wv.z, d.w + m.lambda * wv.w};
+      float wn[4] = {wv.x, wv.y, wv.z, wv.w};
+      if (m.adagrad) {
+        float4 av = ld4(ap);
+        float a[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] += g[i] * g[i];
+          g[i] = g[i] / (m.beta + sqrtf(a[i]));
+        }
+        st4(ap, make_float4(a[0], a[1], a[2], a[3]));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wn[i] -= m.lr * g[i];
+      st4(wp, make_float4(wn[0], wn[1], wn[2], wn[3]));
+    }
+  }
+  // column sums of delta over the block's users -> one reduction per column per block
+  red[threadIdx.y * blockDim.x + threadIdx.x] = d;
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 < ld4n) {
+    float4 s = f4zero();
+    for (int y = 0; y < blockDim.y; ++y) s = add4(s, red[y * blockDim.x + threadIdx.x]);
+    red_add_v4(m.gb + c4 * 4, s);
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int cnt = min((int)blockDim.y, bt.n_users - blockIdx.x * (int)blockDim.y);
+    if (cnt > 0) {
+      red_add_f32(m.g_steps, (float)cnt);
+      atomicAdd(&stats->user_steps, (unsigned long long)cnt);
+    }
+  }
+}
+
+// H8 item part, cdae.hpp:333-349: every kept input row j gets
+// gW[j] += scale*([Uu[u] (.)] delta) + lambda*W[j]; with linear_function also
+// GU[u] += delta (.) W[j] (:340).  One warp per input chunk, same geometry as gather_kernel.
+template <int G, int NV>
+__global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
+  using RM = RowMap<G, NV>;
+  constexpr int NG = RM::NG, UNR = 4;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= bt.n_in_items) return;
+  const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+  const WorkItem wi = load_item(bt.in_items + warp);
+  const int32_t* items = bt.col + wi.s0;
+  const uint8_t* keep = bt.keep + wi.aux0;
+  float4 d[NV], sd[NV], gu[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = RM::col4(gl, v);
+    d[v] = c < m.ld ? ld4(bt.D + (int64_t)wi.u_local * m.ld + c) : f4zero();
+    sd[v] = scale4(m.scale, d[v]);
+    if (m.linear_function && c < m.ld) sd[v] = mul4(ld4(m.Uu + (int64_t)wi.uid * m.ld + c), sd[v]);
+    gu[v] = f4zero();
+  }
+  for (int base = 0; base < wi.n; base += NG * UNR) {
+    int it[UNR];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      const int r = base + t * NG + grp;
+      it[t] = (r < wi.n && keep[r]) ? __ldg(items + r) : -1;
+    }
+    float4 w[UNR][NV];
+#pragma unroll
+    for (int t = 0; t < UNR; ++t)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = RM::col4(gl, v);
+        w[t][v] = (it[t] >= 0 && c < m.ld) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+      }
+#pragma unroll
+    for (int t = 0; t < UNR; ++t) {
+      if (it[t] < 0) continue;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = RM::col4(gl, v);
+        if (c < m.ld) red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, fma4(m.lambda, w[t][v], sd[v]));
+        if (m.linear_function) gu[v] = add4(gu[v], mul4(d[v], w[t][v]));
+      }
+    }
+  }
+  if (m.linear_function) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      gu[v] = cross_group_sum<G>(gu[v]);
+      const int c = RM::col4(gl, v);
+      if (grp == 0 && c < m.ld) red_add_v4(bt.GU + (int64_t)wi.u_local * m.ld + c, gu[v]);
+    }
+  }
+}
+
+// cdae.hpp:295-299,351-357: Uu[u] takes upd(lambda*Uu[u] + GU[u]) (linear_function only).
+__global__ void __launch_bounds__(256) uu_update_kernel(ModelDev m, BatchDev bt) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)bt.n_users * m.ld) return;
+  const int u = (int)(idx / m.ld), c = (int)(idx % m.ld);
+  const int64_t uid = bt.uids[u];
+  float* wp = m.Uu + uid * m.ld + c;
+  float g = m.lambda * (*wp) + bt.GU[idx];
+  if (c >= m.K) g = 0.f;
+  if (m.adagrad) {
+    float* ap = m.Uu_ag + uid * m.ld + c;
+    const float a = *ap + g * g;
+    *ap = a;
+    g = g / (m.beta + sqrtf(a));
+  }
+  *wp -= m.lr * g;
+}
+
+// ---------------------------------------------------------------------------------------
+// H9, the upd() inlined at every update site of the reference (e.g. cdae.hpp:253-257):
+// acc += g^2; g /= beta + sqrt(acc); w -= lr*g — applied ONCE per element with the summed
+// minibatch gradient, then the accumulator is cleared.  Elements whose gradient is exactly 0
+// are left untouched (upd with g = 0 is a no-op), so the dense pass equals "touched rows only".
+struct ApplySeg {
+  float *w, *acc, *g;
+  int64_t n4;        // float4 count
+  float extra_coef;  // b only: g += extra_coef * n_steps * w   (n * lambda * b)
+};
+struct ApplyArgs {
+  ApplySeg seg[4];
+  int nseg;
+  float lr, beta;
+  int adagrad;
+  const float* g_steps;
+};
+__global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
+  const float steps = *a.g_steps;
+  for (int s = 0; s < a.nseg; ++s) {
+    const ApplySeg sg = a.seg[s];
+    const float extra = sg.extra_coef * steps;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      float4 g4 = ld4(sg.g + i * 4);
+      if (extra == 0.f && g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) continue;
+      float4 w4 = ld4(sg.w + i * 4);
+      float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      float w[4] = {w4.x, w4.y, w4.z, w4.w};
+      if (extra != 0.f) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[k] += extra * w[k];
+      }
+      if (a.adagrad) {
+        float4 a4 = ld4(sg.acc + i * 4);
+        float ac[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ac[k] += g[k] * g[k];
+          g[k] = g[k] / (a.beta + sqrtf(ac[k]));
+        }
+        st4(sg.acc + i * 4, make_float4(ac[0], ac[1], ac[2], ac[3]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
+      st4(sg.w + i * 4, make_float4(w[0], w[1], w[2], w[3]));
+      st4(sg.g + i * 4, f4zero());
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// parameter plumbing
+// CDAE::reset's Random(rows,K)*4*sqrt(6/(I+K)) (cdae.hpp:112-121) from Philox:
+// element idx (row*K+k, unpadded) of block `which` = float((2u-1)*scale),
+// u = (word+0.5)*2^-32, word = philox(seed, {idx lo, idx hi, which, 0xC0DE}).x
+__global__ void init_uniform_kernel(float* dst, int64_t rows, int K, int ld, double scale,
+                                    uint64_t seed, uint32_t which) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  const Philox4 p = philox4x32(seed, (uint32_t)i, (uint32_t)((uint64_t)i >> 32), which, 0xC0DEu);
+  const double u = ((double)p.x + 0.5) * (1.0 / 4294967296.0);
+  dst[r * ld + k] = (float)((2. * u - 1.) * scale);
+}
+__global__ void fill_kernel(float* dst, int64_t rows, int K, int ld, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  dst[i] = (int)(i % ld) < K ? v : 0.f;
+}
+// padded fp32 [rows][ld] <-> dense fp64 [rows][K]
+__global__ void pack_from_double_kernel(float* dst, const double* src, int64_t rows, int K, int ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int64_t r = i / ld;
+  const int k = (int)(i % ld);
+  dst[i] = k < K ? (float)src[r * K + k] : 0.f;
+}
+__global__ void unpack_to_double_kernel(double* dst, const float* src, int64_t rows, int K, int ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  dst[i] = (double)src[r * ld + k];
+}
+__global__ void unpack_to_float_kernel(float* dst, const float* src, int64_t rows, int K, int ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  dst[i] = src[r * ld + k];
+}
+// Process-group read-back of user-private tables: copy the rows this rank trains (its slice of
+// each global minibatch of B users), zero the others; a sum across ranks then yields the table.
+__global__ void owned_rows_kernel(float* dst, const float* src, int64_t rows, int ld, int64_t B,
+                                  int64_t U, int rank, int world) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int64_t uid = i / ld;
+  const int64_t lo = (uid / B) * B;
+  const int64_t n = min(B, U - lo);
+  const int64_t a = lo + (n * rank) / world, b = lo + (n * (rank + 1)) / world;
+  dst[i] = (uid >= a && uid < b) ? src[i] : 0.f;
+}
+
+// sum of squares, double accumulation (CDAE::penalty_loss, cdae.hpp:103-107 / penalty.hpp:36-39)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* src, int64_t n, double* out) {
+  double s = 0.;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = src[i];
+    s += v * v;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    atomicAdd(out, t);
+  }
+}
+
+}  // namespace cdae

@@ -1,0 +1,202 @@
+/* cdae_b200.h — C ABI of the B200-native CDAE training / scoring engine.
+ *
+ * This is the drop-in boundary for the hot path of jasonyaw/CDAE (libcf), i.e. everything
+ * `class CDAE` (src/model/recsys/cdae.hpp) computes.  The reference has no FFI for this path
+ * (it is a header-only C++ class that Solver<Model> / TOPN_Evaluation<Model> duck-type
+ * against), so each entry point below names the reference member function
+ * whose work it takes over; the host-side `libcf::CDAE` in cdae_b200/host/ keeps the
+ * reference's class surface and is a thin caller of these functions.
+ *
+ * Conventions
+ *  - plain C: opaque handle, pointers + sizes, no C++ / torch types.
+ *  - every function returns 0 on success, a negative CDAE_E_* code otherwise;
+ *    cdae_last_error() returns a thread-local message for the last failure.  (The reference's
+ *    convention is glog CHECK -> abort, cdae.hpp:83,139,187; the host class maps a non-zero
+ *    return to LOG(FATAL) to keep that behaviour.)
+ *  - all host buffers are caller-owned and may be pageable or pinned (cdae_host_alloc gives
+ *    pinned memory); device memory is owned by the handle.
+ *  - one handle is driven by one host thread at a time, except cdae_topn_lookup, which only
+ *    reads the table cdae_topn_build produced and is safe to call concurrently (the reference
+ *    calls recommend() from ThreadPool workers, evaluation.hpp:137-158).
+ *  - parameters live on the device in fp32 (the reference keeps fp64 Eigen matrices,
+ *    base/mat.hpp:12,19-22); the boundary exchanges them as row-major doubles, the
+ *    reference's own type.
+ *  - CSR rows must be strictly ascending (needed for the on-device negative sampler);
+ *    every user that is trained must have >= 1 item (CHECK at cdae.hpp:139).
+ */
+#ifndef CDAE_B200_H_
+#define CDAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDAE_B200_ABI_VERSION 1
+
+/* error codes */
+#define CDAE_OK 0
+#define CDAE_E_INVALID (-1)     /* bad argument / shape / unsupported configuration */
+#define CDAE_E_CUDA (-2)        /* CUDA runtime error (message has the CUDA string) */
+#define CDAE_E_NCCL (-3)        /* NCCL error or NCCL not loadable */
+#define CDAE_E_STATE (-4)       /* call order (e.g. topn_lookup before topn_build) */
+#define CDAE_E_NUMERIC (-5)     /* LOGISTIC loss fed a score outside (0,1): reference aborts (loss.hpp:96) */
+
+/* libcf::LossType, src/model/loss.hpp:10-18 */
+enum cdae_loss {
+  CDAE_LOSS_SQUARE = 0, CDAE_LOSS_LOGISTIC = 1, CDAE_LOSS_LOG = 2, CDAE_LOSS_HINGE = 3,
+  CDAE_LOSS_SQUARED_HINGE = 4, CDAE_LOSS_CROSS_ENTROPY = 5, CDAE_LOSS_LOGM = 6
+};
+
+/* parameter blocks of class CDAE (cdae.hpp:430-439); *_AG are the AdaGrad accumulators */
+enum cdae_param {
+  CDAE_P_W = 0,     /* I x K  encoder (and, tied, decoder) item weights            */
+  CDAE_P_V,         /* I x K  decoder item weights, only when asymmetric           */
+  CDAE_P_WU,        /* U x K  per-user input embedding, only when user_factor      */
+  CDAE_P_B,         /* K      hidden bias                                          */
+  CDAE_P_BPRIME,    /* I      output bias                                          */
+  CDAE_P_UU,        /* U x K  per-user multiplicative map, only when linear_function */
+  CDAE_P_W_AG, CDAE_P_V_AG, CDAE_P_WU_AG, CDAE_P_B_AG, CDAE_P_BPRIME_AG, CDAE_P_UU_AG,
+  CDAE_P_COUNT
+};
+
+/* libcf::CDAEConfig (cdae.hpp:13-31) + device options.  Fill with cdae_config_default()
+ * first; fields added by later ABI versions then keep their defaults. */
+typedef struct cdae_config {
+  double lambda;              /* L2 coefficient, applied per touched row per occurrence */
+  double learn_rate;
+  double corruption_ratio;    /* q: an input item is kept iff uniform > q (cdae.hpp:366) */
+  double beta;                /* AdaGrad denominator offset: g / (beta + sqrt(acc))      */
+  int32_t loss_type;          /* enum cdae_loss */
+  int32_t num_dim;            /* K */
+  int32_t num_neg;            /* negatives per positive */
+  int32_t num_corruptions;
+  int32_t using_adagrad;      /* 0: plain SGD */
+  int32_t asymmetric;         /* 0: tied weights (decoder = W), 1: separate V */
+  int32_t user_factor;
+  int32_t linear;             /* identity activation */
+  int32_t scaled;             /* scale inputs by 1/(1-q) */
+  int32_t linear_function;
+  int32_t tanh_act;
+  /* ---- device options (no reference counterpart) ---- */
+  int32_t batch_users;        /* users per frozen minibatch; 0 -> 8192.  1 reproduces the
+                                 reference's per-user online step. */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t reserved[7];
+} cdae_config_t;
+
+typedef struct cdae_epoch_stats {
+  int64_t user_steps;         /* (user, corruption) pairs trained                     */
+  int64_t outputs;            /* positives + negatives scored                          */
+  int64_t inputs_kept;        /* input items that survived corruption                  */
+  double loss_sum;            /* sum over scored outputs of loss(y, t)                 */
+  double device_ms;           /* device time of the call, CUDA events on the handle's stream */
+  int64_t kernel_launches;    /* kernels this call launched                            */
+  int64_t h2d_bytes, d2h_bytes; /* bytes this call copied across PCIe                  */
+} cdae_epoch_stats_t;
+
+typedef struct cdae_handle cdae_handle;
+
+int cdae_abi_version(void);
+const char* cdae_last_error(void);
+
+/* CDAEConfig() defaults (cdae.hpp:14-30): lambda .01, lr .1, LOGISTIC, K 10, adagrad, q .5,
+ * cnum 1, tied, user_factor, sigmoid, num_neg 5, scaled, beta 0. */
+int cdae_config_default(cdae_config_t* cfg);
+
+/* CDAE::CDAE + CDAE::reset (cdae.hpp:39-74,109-134; RecsysModelBase::reset,
+ * recsys_model_base.hpp:29-34): takes the user->items structure the reference builds with
+ * Data::get_feature_pair_label_hashtable(0,1) as CSR, uploads it, allocates parameters
+ * (accumulators 1e-4, b = b' = 0, Uu = 1; W, V, Wu zero until cdae_init_params / cdae_set_param). */
+int cdae_create(const cdae_config_t* cfg, int64_t num_users, int64_t num_items,
+                const int64_t* row_ptr, const int32_t* col_idx, cdae_handle** out);
+int cdae_destroy(cdae_handle* h);
+
+/* The Random(I,K) * 4*sqrt(6/(I+K)) draw of CDAE::reset (cdae.hpp:112-121), from a
+ * counter-based Philox stream instead of rand() (values documented in DESIGN.md). */
+int cdae_init_params(cdae_handle* h, uint64_t seed);
+
+/* No reference counterpart (parameters are private there, cdae.hpp:428): read / write one
+ * block as row-major doubles.  n must equal rows*cols of the block; absent blocks have n = 0. */
+int cdae_param_shape(cdae_handle* h, int which, int64_t* rows, int64_t* cols);
+int cdae_set_param(cdae_handle* h, int which, const double* src, int64_t n);
+int cdae_get_param(cdae_handle* h, int which, double* dst, int64_t n);
+
+/* CDAE::train_one_iteration (cdae.hpp:136-146): one pass over users [0,U) in minibatches of
+ * batch_users, masks and negatives from Philox(seed, epoch) (spec in DESIGN.md; identical
+ * on any GPU count).  In a process group (cdae_dist_init) each rank trains its shard of every
+ * minibatch and the dense item-side gradients are all-reduced once per minibatch. */
+int cdae_train_epoch(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats);
+
+/* Same, with the training CSR taken from HOST memory on every call, the way
+ * train_one_iteration(const Data&) receives its data each epoch.  Shapes must match
+ * cdae_create (same U; nnz may differ).  H2D copy and the D2H read of stats are inside
+ * the call. */
+int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* col_idx,
+                         uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats);
+
+/* CDAE::train_one_user_corruption (cdae.hpp:198-358) for n DISTINCT users as ONE frozen
+ * minibatch with EXPLICIT randomness: keep_mask has one byte per train item of each listed
+ * user (CSR order, concatenated); negatives has n_u*num_neg item ids per user, concatenated
+ * (each must be outside that user's row).  n = 1 is the reference's online step. */
+int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* keep_mask,
+                     const int32_t* negatives, cdae_epoch_stats_t* stats);
+
+/* CDAE::get_hidden_values (cdae.hpp:373-416) for n users: z_out is n x K floats.
+ * keep_mask NULL -> uncorrupted input; scale multiplies the summed rows (the reference
+ * passes 1/(1-q) when scaled, 1 otherwise).  Covers get_user_representations (cdae.hpp:148). */
+int cdae_encode(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* keep_mask,
+                double scale, float* z_out);
+
+/* CDAE::data_loss (cdae.hpp:78-101): fresh Philox corruption, sum over users of the loss of
+ * their positives, averaged over num_corruptions.  CDAE::penalty_loss (cdae.hpp:103-107). */
+int cdae_data_loss(cdae_handle* h, uint64_t seed, double* out);
+int cdae_penalty_loss(cdae_handle* h, double* out);
+
+/* CDAE::recommend (cdae.hpp:162-196) for ALL users at once — the batch point is the
+ * pre_recommend() hook (recsys_model_base.hpp:72, evaluation.hpp:135).  Scores every item
+ * against every user's uncorrupted hidden vector, skips the user's train items, keeps the
+ * top-k by the reference's rule (strict improvement, ties keep the lower id), ids sorted by
+ * score descending.  cdae_topn_lookup copies one user's list (thread-safe). */
+int cdae_topn_build(cdae_handle* h, int32_t topk);
+int cdae_topn_lookup(cdae_handle* h, int64_t uid, int64_t* ids_out, float* scores_out);
+/* Whole table, U x topk (ids) and U x topk (scores; nullable). */
+int cdae_topn_fetch(cdae_handle* h, int64_t* ids_out, float* scores_out);
+/* TOPN_Evaluation::evaluate (evaluation.hpp:113-181) on the built table against a test CSR:
+ * out8 = P@1,P@5,P@10,R@1,R@5,R@10,MAP@5,MAP@10 averaged over users with test items. */
+int cdae_topn_evaluate(cdae_handle* h, const int64_t* test_row_ptr, const int32_t* test_col,
+                       double* out8, int64_t* users_evaluated);
+
+/* Data parallelism over the GPUs of one node: one process per GPU, each owning the user
+ * shard [rank*U/world, (rank+1)*U/world) of every minibatch; item-side parameters are
+ * replicated and kept identical by all-reducing the dense gradients.  nccl_unique_id is
+ * the 128-byte ncclUniqueId created on rank 0 (cdae_dist_unique_id) and distributed by the
+ * caller (torch.distributed / MPI / a file). */
+int cdae_dist_unique_id(void* id128_out);
+int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id);
+
+/* Per-kernel-class device timing for benchmarks: when enabled, every kernel launch is
+ * bracketed by CUDA events on the handle's stream; cdae_profile_get returns, per class,
+ * the summed milliseconds and the number of launches since cdae_profile(h, 1). */
+enum cdae_kernel_class {
+  CDAE_K_SAMPLE = 0, CDAE_K_GATHER, CDAE_K_ACTIVATE, CDAE_K_DECODE, CDAE_K_HIDDEN_BWD,
+  CDAE_K_SCATTER, CDAE_K_ALLREDUCE, CDAE_K_APPLY, CDAE_K_TOPN, CDAE_K_COUNT
+};
+int cdae_profile(cdae_handle* h, int32_t enable);
+int cdae_profile_get(cdae_handle* h, double* ms_out /*[CDAE_K_COUNT]*/,
+                     int64_t* launches_out /*[CDAE_K_COUNT]*/);
+
+/* pinned host memory for buffers that cross the boundary every step */
+int cdae_host_alloc(void** ptr, int64_t bytes);
+int cdae_host_free(void* ptr);
+
+/* Blocks until all work queued on the handle's stream has finished. */
+int cdae_synchronize(cdae_handle* h);
+/* The handle's CUDA stream (cudaStream_t as void*), for callers that time with their own events. */
+int cdae_stream(cdae_handle* h, void** stream_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDAE_B200_H_ */
