@@ -280,16 +280,23 @@ static BatchDev make_batch(cdae_handle* h, const WorkItem* in, int64_t n_in, con
   return bt;
 }
 
-// launch one of the <G,NV> row-geometry instantiations by leading dimension
-#define DISPATCH_LD(ld, CALL)                                  \
-  do {                                                         \
-    if ((ld) <= 16) { CALL(4, 1); }                            \
-    else if ((ld) <= 32) { CALL(8, 1); }                       \
-    else if ((ld) <= 64) { CALL(16, 1); }                      \
-    else if ((ld) <= 128) { CALL(32, 1); }                     \
-    else if ((ld) <= 256) { CALL(32, 2); }                     \
-    else if ((ld) <= 384) { CALL(32, 3); }                     \
-    else { CALL(32, 4); }                                      \
+// launch one of the <G,NV> row-geometry instantiations by leading dimension:
+// n4 = ld/4 vectors per row, G = smallest power of two with 4*G >= n4, NV = ceil(n4/G) in 2..4
+#define DISPATCH_LD(ld, CALL)                                          \
+  do {                                                                 \
+    const int n4__ = (ld) / 4;                                         \
+    if (n4__ <= 2) { CALL(1, 2); }                                     \
+    else if (n4__ <= 4) { CALL(1, 4); }                                \
+    else if (n4__ <= 6) { CALL(2, 3); }                                \
+    else if (n4__ <= 8) { CALL(2, 4); }                                \
+    else if (n4__ <= 12) { CALL(4, 3); }                               \
+    else if (n4__ <= 16) { CALL(4, 4); }                               \
+    else if (n4__ <= 24) { CALL(8, 3); }                               \
+    else if (n4__ <= 32) { CALL(8, 4); }                               \
+    else if (n4__ <= 48) { CALL(16, 3); }                              \
+    else if (n4__ <= 64) { CALL(16, 4); }                              \
+    else if (n4__ <= 96) { CALL(32, 3); }                              \
+    else { CALL(32, 4); }                                              \
   } while (0)
 
 static int launch_gather(cdae_handle* h, const BatchDev& bt) {

@@ -95,22 +95,26 @@ enum { LOSS_SQUARE = 0, LOSS_LOGISTIC = 1, LOSS_LOG = 2, LOSS_HINGE = 3, LOSS_SQ
        LOSS_CE = 5, LOSS_LOGM = 6 };
 
 // Returns dl/dy; *loss receives l(y, t).  `bad` is set for LOGISTIC outside its domain
-// (the reference CHECK-aborts, loss.hpp:85,96).
+// (the reference CHECK-aborts, loss.hpp:85,96).  The two losses that are meaningful for CDAE
+//  use the SFU exp/log (ex2.approx / lg2.approx, |rel err| ~ 2^-21 over
+// the clamped range |y| <= 18) — the decode kernel is issue-bound and libm's expf/log1pf cost
+// ~40 instructions per output.
 __device__ __forceinline__ float loss_grad(int lt, float y, float t, float* loss, int* bad) {
   switch (lt) {
     case LOSS_CE: {  // loss.hpp:132-147
       const float ret = (1.f - t) * y;
       if (y > 18.f) {
-        *loss = ret + expf(-y);
+        *loss = ret + __expf(-y);
         return 1.f - t;
       }
       if (y < -18.f) {
         *loss = ret - y;
-        return expf(y) - t;
+        return __expf(y) - t;
       }
-      const float e = expf(-y);
-      *loss = ret + log1pf(e);
-      return 1.f / (1.f + e) - t;
+      const float e = __expf(-y);
+      const float d = 1.f + e;
+      *loss = ret + __logf(d);
+      return __frcp_rn(d) - t;
     }
     case LOSS_LOGISTIC: {  // loss.hpp:84-99
       if (!(y > 0.f && y < 1.f)) {

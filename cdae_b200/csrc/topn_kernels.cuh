@@ -12,20 +12,12 @@
 // path), the fp64 re-rank, and the on-device TOPN_Evaluation metrics (evaluation.hpp:183-219).
 #pragma once
 #include "common.cuh"
+#include "train_kernels.cuh"  // row_contains
 
 namespace cdae {
 
 constexpr int TOPN_M = 64;       // candidates kept per user before the exact re-rank
 constexpr int TOPN_MAX_K = 32;   // largest supported topk
-
-__device__ __forceinline__ bool row_contains(const int32_t* row, int n, int item) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(row + mid) < item) lo = mid + 1; else hi = mid;
-  }
-  return lo < n && __ldg(row + lo) == item;
-}
 
 // Per-user candidate list in shared memory, owned by ONE thread.
 struct CandList {

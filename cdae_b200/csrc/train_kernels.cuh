@@ -4,9 +4,13 @@
 //   sample  -> gather -> activate -> decode -> hidden_backward -> scatter -> apply
 // All item-side tables are row-major [rows][ld] fp32 with ld = round_up(K, 8) (32-byte
 // sectors; pad columns are kept at exactly 0).  A table row is owned by a GROUP of G lanes,
-// each holding NV float4 (column 4*(v*G+lane) .. +3): loads are 16 B per lane and contiguous
-// across the group, the K-reduction is a log2(G)-step shuffle, and a warp works on 32/G rows
-// at once, unrolled UNR deep so that >= 8 independent row loads are in flight per warp.
+// each holding NV <= 4 float4 (column 4*(v*G+lane) .. +3): loads are 16 B per lane and
+// contiguous across the group, the K-reduction is a log2(G)-step shuffle, and a warp works on
+// 32/G rows at once, unrolled UNR deep.  G is the SMALLEST power of two with 16*G >= ld
+// (K=50 -> 4 lanes x 4 vectors, 8 rows per warp instruction): the first version used one
+// vector per lane (16 lanes per row at K=50) and ncu showed it issue-bound (59% issue-active,
+// 29% L2 throughput, DRAM idle — profiles/r01_a_*), so the per-row scalar work (ids, loss,
+// shuffles, addressing) is now amortised over 4x more rows per instruction.
 //
 // Reference lines each kernel takes over are cited at the kernel.
 #pragma once
@@ -49,7 +53,8 @@ struct StatsDev {
 
 template <int G, int NV>
 struct RowMap {
-  static constexpr int NG = 32 / G;  // rows a warp handles at once
+  static constexpr int NG = 32 / G;         // rows a warp handles at once
+  static constexpr int UNR = G == 1 ? 1 : 2;  // row batches in flight per warp
   __device__ static __forceinline__ int col4(int gl, int v) { return (v * G + gl) * 4; }
 };
 
@@ -82,6 +87,16 @@ __device__ __forceinline__ WorkItem load_item(const WorkItem* p) {
   return w;
 }
 
+// membership test in an ascending CSR row
+__device__ __forceinline__ bool row_contains(const int32_t* row, int n, int item) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(row + mid) < item) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && __ldg(row + lo) == item;
+}
+
 // ---------------------------------------------------------------------------------------
 // H3 + H5: corruption mask (cdae.hpp:361-371: keep iff uniform > q) and negative sampling
 // (recsys_model_base.hpp:46-57: uniform item, redraw while it is one of the user's positives;
@@ -91,44 +106,66 @@ __global__ void __launch_bounds__(256) sample_kernel(BatchDev bt, int nu, int64_
                                                      int keep_mode /*0 all,1 none,2 philox*/,
                                                      StatsDev* stats) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= bt.n_in_items) return;
   const int lane = threadIdx.x & 31;
-  const WorkItem wi = load_item(bt.in_items + warp);
+  WorkItem wi = load_item(bt.in_items + min(warp, bt.n_in_items - 1));
+  if (warp >= bt.n_in_items) wi.n = 0;  // keep the whole block alive for the block reduction
   const int64_t r0 = __ldg(bt.row_ptr + wi.uid);
   const int n_u = (int)(__ldg(bt.row_ptr + wi.uid + 1) - r0);
   const int32_t* row = bt.col + r0;
   int kept = 0;
-  for (int i = lane; i < wi.n; i += 32) {
-    const int s = wi.row_off + i;  // position inside the user's row
-    uint8_t k;
-    if (keep_mode == 0) k = 1;
-    else if (keep_mode == 1) k = 0;
-    else {
-      const Philox4 p = philox4x32(seed, (uint32_t)wi.uid, (uint32_t)(s >> 2), pass, 0u);
-      k = philox_word(p, s & 3) > keep_thr;
+  // chunks start at multiples of 64 slots, so slots 4q..4q+3 of the chunk share one Philox call
+  for (int q = lane; q * 4 < wi.n; q += 32) {
+    Philox4 p = {0u, 0u, 0u, 0u};
+    if (keep_mode == 2) p = philox4x32(seed, (uint32_t)wi.uid, (uint32_t)((wi.row_off >> 2) + q), pass, 0u);
+    for (int i = q * 4; i < min(q * 4 + 4, wi.n); ++i) {
+      uint8_t k;
+      if (keep_mode == 0) k = 1;
+      else if (keep_mode == 1) k = 0;
+      else k = philox_word(p, i & 3) > keep_thr;  // cdae.hpp:366: keep iff uniform > ratio
+      bt.keep[wi.aux0 + i] = k;
+      kept += k;
     }
-    bt.keep[wi.aux0 + i] = k;
-    kept += k;
   }
+  // Negatives: draw d of the user takes word (d&3) of philox({uid, d>>2, pass, 1}) — one Philox
+  // call serves four draws — and, only if that item is one of the user's positives (probability
+  // n_u/I), retries a = 1,2,.. from word ((a-1)&3) of philox({uid, d, pass, 2 + ((a-1)>>2)}).
+  // Chunks start at multiples of 64 slots, so a lane's quad of draws never straddles a call.
   const int ndraw = wi.n * nu;
   int32_t* out = bt.negs + (int64_t)wi.aux0 * nu;
-  for (int j = lane; j < ndraw; j += 32) {
-    const uint32_t d = (uint32_t)(wi.row_off * nu + j);  // draw index inside the user
-    int32_t item = 0;
-    for (uint32_t a = 0;; ++a) {
-      const Philox4 p = philox4x32(seed, (uint32_t)wi.uid, d, pass, 1u + (a >> 2));
-      item = (int32_t)(((uint64_t)philox_word(p, a & 3) * (uint64_t)I) >> 32);
-      int lo = 0, hi = n_u;  // binary search in the user's ascending row
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(row + mid) < item) lo = mid + 1; else hi = mid;
-      }
-      if (!(lo < n_u && __ldg(row + lo) == item)) break;
+  const uint32_t d_base = (uint32_t)(wi.row_off * nu);
+  const uint32_t d_head = (4u - (d_base & 3u)) & 3u;  // draws before the first aligned quad
+  const int nquad = ((int)d_head > 0 ? 1 : 0) + (ndraw - min((int)d_head, ndraw) + 3) / 4;
+  for (int q = lane; q < nquad; q += 32) {
+    int j0, j1;  // [j0, j1) = this quad's draws inside the chunk
+    if (d_head > 0) {
+      j0 = q == 0 ? 0 : (int)d_head + (q - 1) * 4;
+      j1 = q == 0 ? (int)d_head : j0 + 4;
+    } else {
+      j0 = q * 4;
+      j1 = j0 + 4;
     }
-    out[j] = item;
+    j1 = min(j1, ndraw);
+    if (j0 >= j1) continue;
+    const Philox4 p0 = philox4x32(seed, (uint32_t)wi.uid, (d_base + (uint32_t)j0) >> 2, pass, 1u);
+    for (int j = j0; j < j1; ++j) {
+      const uint32_t d = d_base + (uint32_t)j;
+      int32_t item = (int32_t)(((uint64_t)philox_word(p0, d & 3) * (uint64_t)I) >> 32);
+      for (uint32_t a = 1; row_contains(row, n_u, item); ++a) {
+        const Philox4 p = philox4x32(seed, (uint32_t)wi.uid, d, pass, 2u + ((a - 1) >> 2));
+        item = (int32_t)(((uint64_t)philox_word(p, (a - 1) & 3) * (uint64_t)I) >> 32);
+      }
+      out[j] = item;
+    }
   }
-  kept = (int)group_sum<32>((float)kept);
-  if (lane == 0 && stats) atomicAdd(&stats->inputs_kept, (unsigned long long)kept);
+  if (stats) {  // one atomic per block, not per warp (same-address atomics serialise in L2)
+    __shared__ int kept_s;
+    if (threadIdx.x == 0) kept_s = 0;
+    __syncthreads();
+    kept = (int)group_sum<32>((float)kept);
+    if (lane == 0) atomicAdd(&kept_s, kept);
+    __syncthreads();
+    if (threadIdx.x == 0 && kept_s) atomicAdd(&stats->inputs_kept, (unsigned long long)kept_s);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -138,7 +175,7 @@ __global__ void __launch_bounds__(256) sample_kernel(BatchDev bt, int nu, int64_
 template <int G, int NV>
 __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt) {
   using RM = RowMap<G, NV>;
-  constexpr int NG = RM::NG, UNR = 4;
+  constexpr int NG = RM::NG, UNR = RM::UNR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= bt.n_in_items) return;
   const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
@@ -206,11 +243,18 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
 template <int G, int NV, bool TRAIN>
 __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, StatsDev* stats) {
   using RM = RowMap<G, NV>;
-  constexpr int NG = RM::NG, UNR = 4;
+  constexpr int NG = RM::NG, UNR = RM::UNR;
+  __shared__ float blk_loss;
+  __shared__ int blk_out;
+  if (threadIdx.x == 0) {
+    blk_loss = 0.f;
+    blk_out = 0;
+  }
+  __syncthreads();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= bt.n_out_items) return;
   const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
-  const WorkItem wi = load_item(bt.out_items + warp);
+  WorkItem wi = load_item(bt.out_items + min(warp, bt.n_out_items - 1));
+  if (warp >= bt.n_out_items) wi.n = 0;  // idle warp of the last block: no rows, joins the barrier
   const int32_t* pos = bt.col + wi.s0;
   const uint8_t* keep = bt.keep + wi.aux0;
   const int32_t* neg = bt.negs + (int64_t)wi.aux0 * m.nu;
@@ -287,7 +331,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, St
       if (gl == 0) red_add_f32(m.gbp + it[t], g + m.lambda * bp[t]);
     }
   }
-  if (TRAIN) {
+  if (TRAIN && wi.n > 0) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       hg[v] = cross_group_sum<G>(hg[v]);
@@ -297,10 +341,15 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, St
   }
   loss_acc = group_sum<32>(loss_acc);
   bad = __any_sync(0xffffffffu, bad);
-  if (lane == 0) {
-    atomicAdd(&stats->loss_sum, (double)loss_acc);
-    atomicAdd(&stats->outputs, (unsigned long long)R);
+  if (lane == 0) {  // block-level partials first: same-address global atomics serialise in L2
+    atomicAdd(&blk_loss, loss_acc);
+    atomicAdd(&blk_out, R);
     if (bad) stats->bad_loss = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&stats->loss_sum, (double)blk_loss);
+    atomicAdd(&stats->outputs, (unsigned long long)blk_out);
   }
 }
 
@@ -338,6 +387,7 @@ __global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchD
         float a[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          if (g[i] == 0.f) continue;  // upd(g = 0) is a no-op; also keeps 0/0 out of pad columns
           a[i] += g[i] * g[i];
           g[i] = g[i] / (m.beta + sqrtf(a[i]));
         }
@@ -371,7 +421,7 @@ __global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchD
 template <int G, int NV>
 __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
   using RM = RowMap<G, NV>;
-  constexpr int NG = RM::NG, UNR = 4;
+  constexpr int NG = RM::NG, UNR = RM::UNR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= bt.n_in_items) return;
   const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
@@ -432,6 +482,7 @@ __global__ void __launch_bounds__(256) uu_update_kernel(ModelDev m, BatchDev bt)
   float* wp = m.Uu + uid * m.ld + c;
   float g = m.lambda * (*wp) + bt.GU[idx];
   if (c >= m.K) g = 0.f;
+  if (g == 0.f) return;
   if (m.adagrad) {
     float* ap = m.Uu_ag + uid * m.ld + c;
     const float a = *ap + g * g;
@@ -479,6 +530,7 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
         float ac[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          if (g[k] == 0.f) continue;  // no-op element (and no 0/0 in pad columns when beta = 0)
           ac[k] += g[k] * g[k];
           g[k] = g[k] / (a.beta + sqrtf(ac[k]));
         }

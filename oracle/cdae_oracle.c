@@ -725,15 +725,14 @@ void orc_sample_negatives(const orc_model* m, uint64_t seed, uint32_t pass, int6
                           int64_t* negs) {
   const int64_t n = (m->row_ptr[uid + 1] - m->row_ptr[uid]) * m->cfg.num_neg;
   for (int64_t d = 0; d < n; ++d) {
-    for (uint32_t a = 0;; ++a) {
-      uint32_t r[4];
-      orc_philox4x32(seed, (uint32_t)uid, (uint32_t)d, pass, 1u + (a >> 2), r);
-      int64_t item = (int64_t)(((uint64_t)r[a & 3] * (uint64_t)m->I) >> 32);
-      if (!row_contains(m, uid, item)) {
-        negs[d] = item;
-        break;
-      }
+    uint32_t r[4];
+    orc_philox4x32(seed, (uint32_t)uid, (uint32_t)(d >> 2), pass, 1u, r);
+    int64_t item = (int64_t)(((uint64_t)r[d & 3] * (uint64_t)m->I) >> 32);
+    for (uint32_t a = 1; row_contains(m, uid, item); ++a) {
+      orc_philox4x32(seed, (uint32_t)uid, (uint32_t)d, pass, 2u + ((a - 1) >> 2), r);
+      item = (int64_t)(((uint64_t)r[(a - 1) & 3] * (uint64_t)m->I) >> 32);
     }
+    negs[d] = item;
   }
 }
 

@@ -100,8 +100,9 @@ int64_t orc_topn_evaluate(const orc_model* m, const int64_t* test_row_ptr, const
  * Philox4x32-10, key = (seed lo, seed hi).
  *  keep mask of slot s of user u in pass p: word (s&3) of philox(ctr = {u, s>>2, p, 0});
  *      keep iff word > floor(q*2^32)  (q<=0 keeps all, q>=1 keeps none)
- *  negative draw d of user u in pass p: attempts a=0,1,..: word (a&3) of
- *      philox(ctr = {u, d, p, 1 + (a>>2)}); item = (word * I) >> 32; accept iff not in row u.
+ *  negative draw d of user u in pass p: word (d&3) of philox(ctr = {u, d>>2, p, 1});
+ *      item = (word * I) >> 32; while the item is in row u retry a = 1,2,..: word ((a-1)&3) of
+ *      philox(ctr = {u, d, p, 2 + ((a-1)>>2)}).
  *  pass p = epoch * num_corruptions + corruption index. */
 void orc_philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                     uint32_t out[4]);

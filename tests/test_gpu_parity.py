@@ -2,7 +2,8 @@
 
 Tolerances: the device computes in fp32, the reference in fp64.
   hidden activations   : max relative error <= 1e-4 (north-star bound; measured ~1e-6)
-  parameters after step: |a-b| <= 2e-5 + 2e-4*|b|  (fp32 rounding + atomics order)
+  parameters after step: |a-b| <= 2e-5 + 2e-4*|b|  (fp32 rounding + atomics order);
+                         AdaGrad accumulators 2e-5 + 1e-3*|b|
   top-N lists          : identical ids
 """
 import numpy as np
@@ -14,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 Z_RTOL = 1e-4
 P_RTOL, P_ATOL = 2e-4, 2e-5
+AG_RTOL = 1e-3
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +39,10 @@ def assert_params(m, o, names=None):
         if a.size == 0:
             continue
         b = np.asarray(o[k] if isinstance(o, dict) else o.param(k)).reshape(a.shape)
-        np.testing.assert_allclose(a, b, rtol=P_RTOL, atol=P_ATOL, err_msg=k)
+        # AdaGrad accumulators hold sums of SQUARED summed gradients: twice the relative error
+        # of an fp32 sum taken in atomics order, so they get a wider relative band
+        rtol = AG_RTOL if k.endswith("_ag") else P_RTOL
+        np.testing.assert_allclose(a, b, rtol=rtol, atol=P_ATOL, err_msg=k)
 
 
 @pytest.mark.parametrize("name", golden.NAMES)
