@@ -280,32 +280,37 @@ static BatchDev make_batch(cdae_handle* h, const WorkItem* in, int64_t n_in, con
   return bt;
 }
 
-// launch one of the <G,NV> row-geometry instantiations by leading dimension:
-// n4 = ld/4 vectors per row, G = smallest power of two with 4*G >= n4, NV = ceil(n4/G) in 2..4
+// launch one of the <G,NV> row-geometry instantiations by leading dimension (ld is a multiple
+// of 32 floats): a warp-level 16-byte access covers one 128-byte line per row with G = 8 lanes,
+// two lines with 16, four with 32; NV = vectors per lane.
 #define DISPATCH_LD(ld, CALL)                                          \
   do {                                                                 \
-    const int n4__ = (ld) / 4;                                         \
-    if (n4__ <= 2) { CALL(1, 2); }                                     \
-    else if (n4__ <= 4) { CALL(1, 4); }                                \
-    else if (n4__ <= 6) { CALL(2, 3); }                                \
-    else if (n4__ <= 8) { CALL(2, 4); }                                \
-    else if (n4__ <= 12) { CALL(4, 3); }                               \
-    else if (n4__ <= 16) { CALL(4, 4); }                               \
-    else if (n4__ <= 24) { CALL(8, 3); }                               \
-    else if (n4__ <= 32) { CALL(8, 4); }                               \
-    else if (n4__ <= 48) { CALL(16, 3); }                              \
-    else if (n4__ <= 64) { CALL(16, 4); }                              \
-    else if (n4__ <= 96) { CALL(32, 3); }                              \
+    const int lines__ = (ld) / 32;                                     \
+    if (lines__ <= 1) { CALL(8, 1); }                                  \
+    else if (lines__ <= 2) { CALL(8, 2); }                             \
+    else if (lines__ <= 3) { CALL(8, 3); }                             \
+    else if (lines__ <= 4) { CALL(8, 4); }                             \
+    else if (lines__ <= 6) { CALL(16, 3); }                            \
+    else if (lines__ <= 8) { CALL(16, 4); }                            \
+    else if (lines__ <= 12) { CALL(32, 3); }                           \
     else { CALL(32, 4); }                                              \
   } while (0)
 
-static int launch_gather(cdae_handle* h, const BatchDev& bt) {
+static int launch_gather(cdae_handle* h, const BatchDev& bt, const SampleArgs* sa, bool count_kept) {
   if (bt.n_in_items == 0) return 0;
   ProfScope ps(h, CDAE_K_GATHER);
   const int grid = cdiv((int64_t)bt.n_in_items * 32, 256);
-#define CALL(G, NV) gather_kernel<G, NV><<<grid, 256, 0, h->stream>>>(h->m, bt)
-  DISPATCH_LD(h->ld, CALL);
+  StatsDev* st = count_kept ? h->stats_d : nullptr;
+  if (sa) {
+#define CALL(G, NV) gather_kernel<G, NV, true><<<grid, 256, 0, h->stream>>>(h->m, bt, *sa, st)
+    DISPATCH_LD(h->ld, CALL);
 #undef CALL
+  } else {
+    SampleArgs none{};
+#define CALL(G, NV) gather_kernel<G, NV, false><<<grid, 256, 0, h->stream>>>(h->m, bt, none, st)
+    DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  }
   KERNEL_OK(h);
   return 0;
 }
@@ -319,16 +324,21 @@ static int launch_scatter(cdae_handle* h, const BatchDev& bt) {
   KERNEL_OK(h);
   return 0;
 }
-static int launch_decode(cdae_handle* h, const BatchDev& bt, bool train) {
+static int launch_decode(cdae_handle* h, const BatchDev& bt, bool train, const SampleArgs* sa) {
   if (bt.n_out_items == 0) return 0;
   ProfScope ps(h, CDAE_K_DECODE);
   const int grid = cdiv((int64_t)bt.n_out_items * 32, 256);
-  if (train) {
-#define CALL(G, NV) decode_kernel<G, NV, true><<<grid, 256, 0, h->stream>>>(h->m, bt, h->stats_d)
+  SampleArgs none{};
+  if (train && sa) {
+#define CALL(G, NV) decode_kernel<G, NV, true, true><<<grid, 256, 0, h->stream>>>(h->m, bt, *sa, h->stats_d)
+    DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  } else if (train) {
+#define CALL(G, NV) decode_kernel<G, NV, true, false><<<grid, 256, 0, h->stream>>>(h->m, bt, none, h->stats_d)
     DISPATCH_LD(h->ld, CALL);
 #undef CALL
   } else {
-#define CALL(G, NV) decode_kernel<G, NV, false><<<grid, 256, 0, h->stream>>>(h->m, bt, h->stats_d)
+#define CALL(G, NV) decode_kernel<G, NV, false, false><<<grid, 256, 0, h->stream>>>(h->m, bt, none, h->stats_d)
     DISPATCH_LD(h->ld, CALL);
 #undef CALL
   }
@@ -342,29 +352,26 @@ static int launch_activate(cdae_handle* h, const BatchDev& bt, float scale) {
   KERNEL_OK(h);
   return 0;
 }
-static int launch_sample(cdae_handle* h, const BatchDev& bt, uint64_t seed, uint32_t pass,
-                         bool need_negs, bool count_kept) {
-  if (bt.n_in_items == 0) return 0;
-  ProfScope ps(h, CDAE_K_SAMPLE);
+static SampleArgs make_sample_args(cdae_handle* h, uint64_t seed, uint32_t pass) {
+  SampleArgs sa;
+  sa.seed = seed;
+  sa.pass = pass;
   const double q = h->cfg.corruption_ratio;
-  int mode = 2;
-  uint32_t thr = 0;
-  if (q <= 0.) mode = 0;
-  else if (q >= 1.) mode = 1;
-  else thr = (uint32_t)std::floor(q * 4294967296.0);
-  sample_kernel<<<cdiv((int64_t)bt.n_in_items * 32, 256), 256, 0, h->stream>>>(
-      bt, need_negs ? h->cfg.num_neg : 0, h->I, seed, pass, thr, mode, count_kept ? h->stats_d : nullptr);
-  KERNEL_OK(h);
-  return 0;
+  sa.keep_mode = 2;
+  sa.keep_thr = 0;
+  if (q <= 0.) sa.keep_mode = 0;
+  else if (q >= 1.) sa.keep_mode = 1;
+  else sa.keep_thr = (uint32_t)std::floor(q * 4294967296.0);
+  return sa;
 }
 
 // gather -> activate -> decode -> hidden_backward -> scatter -> [all-reduce] -> apply
-static int run_train_minibatch(cdae_handle* h, const BatchDev& bt) {
+static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleArgs* sa) {
   const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
   CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per * (h->m.linear_function ? 3 : 2), h->stream));
-  TRY(launch_gather(h, bt));
+  TRY(launch_gather(h, bt, sa, true));
   TRY(launch_activate(h, bt, h->m.scale));
-  TRY(launch_decode(h, bt, true));
+  TRY(launch_decode(h, bt, true, sa));
   if (bt.n_users > 0) {
     ProfScope ps(h, CDAE_K_HIDDEN_BWD);
     const int bx = h->ld / 4, by = std::max(1, 256 / bx);
@@ -385,13 +392,14 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt) {
   ApplyArgs a;
   a.nseg = 0;
   a.lr = h->m.lr; a.beta = h->m.beta; a.adagrad = h->m.adagrad; a.g_steps = h->m.g_steps;
+  a.steps_slot = h->m.steps_slot;
   a.seg[a.nseg++] = ApplySeg{h->m.W, h->m.W_ag, h->m.gW, h->I * h->ld / 4, 0.f};
   if (h->m.asym) a.seg[a.nseg++] = ApplySeg{h->m.V, h->m.V_ag, h->m.gV, h->I * h->ld / 4, 0.f};
   a.seg[a.nseg++] = ApplySeg{h->m.bp, h->m.bp_ag, h->m.gbp, h->I4 / 4, 0.f};
   a.seg[a.nseg++] = ApplySeg{h->m.b, h->m.b_ag, h->m.gb, h->ld / 4, h->m.lambda};
   apply_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(a);
   KERNEL_OK(h);
-  CU(cudaMemsetAsync(h->m.g_steps, 0, sizeof(float) * 4, h->stream));
+  h->m.steps_slot ^= 1;  // apply cleared the other slot for the next minibatch
   return 0;
 }
 
@@ -412,10 +420,17 @@ static int end_call(cdae_handle* h, cdae_epoch_stats_t* stats) {
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   if (stats) {
+    double loss = 0.;
+    unsigned long long outs = 0, kept = 0;
+    for (int i = 0; i < STAT_STRIPES; ++i) {
+      loss += h->stats_h->loss_sum[i];
+      outs += h->stats_h->outputs[i];
+      kept += h->stats_h->inputs_kept[i];
+    }
     stats->user_steps = (int64_t)h->stats_h->user_steps;
-    stats->outputs = (int64_t)h->stats_h->outputs;
-    stats->inputs_kept = (int64_t)h->stats_h->inputs_kept;
-    stats->loss_sum = h->stats_h->loss_sum;
+    stats->outputs = (int64_t)outs;
+    stats->inputs_kept = (int64_t)kept;
+    stats->loss_sum = loss;
     stats->device_ms = ms;
     stats->kernel_launches = h->launches;
     stats->h2d_bytes = h->h2d;
@@ -449,7 +464,8 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   if (!cfg || !row_ptr || !out || (!col && row_ptr[U] > 0)) return set_error(CDAE_E_INVALID, "NULL argument");
   if (U <= 0 || I <= 0 || U > 0x7fffffff || I > 0x7fffffff) return set_error(CDAE_E_INVALID, "need 0 < U, I < 2^31");
   if (cfg->num_dim < 1 || cfg->num_dim > 512) return set_error(CDAE_E_INVALID, "num_dim must be in [1,512]");
-  if (cfg->num_neg < 0 || cfg->num_corruptions < 1) return set_error(CDAE_E_INVALID, "num_neg >= 0 and num_corruptions >= 1 required");
+  if (cfg->num_neg < 0 || cfg->num_neg > DECODE_MAX_NEGS || cfg->num_corruptions < 1)
+    return set_error(CDAE_E_INVALID, "0 <= num_neg <= %d and num_corruptions >= 1 required", DECODE_MAX_NEGS);
   if (cfg->loss_type < 0 || cfg->loss_type > CDAE_LOSS_LOGM) return set_error(CDAE_E_INVALID, "unknown loss_type %d", cfg->loss_type);
   if (row_ptr[U] >= 0x7fffffff) return set_error(CDAE_E_INVALID, "nnz must be < 2^31");
   TRY(validate_csr(U, I, row_ptr, col));
@@ -461,7 +477,7 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   cdae_handle* h = new cdae_handle();
   h->cfg = *cfg;
   h->U = U; h->I = I; h->K = cfg->num_dim;
-  h->ld = (int)round_up(cfg->num_dim, 8);
+  h->ld = (int)round_up(cfg->num_dim, 32);  // rows are whole 128-byte lines
   h->I4 = round_up(I, 4);
   h->nnz = row_ptr[U];
   h->batch_users = cfg->batch_users > 0 ? cfg->batch_users : 8192;
@@ -644,8 +660,8 @@ static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_e
     for (int c = 0; c < cnum; ++c) {
       BatchDev bt = make_batch(h, h->plan_in.p + p.in0, p.n_in, h->plan_out.p + p.out0, p.n_out,
                                h->plan_uids.p + p.user0, p.n_users);
-      TRY(launch_sample(h, bt, seed, (uint32_t)(epoch * cnum + c), true, true));
-      TRY(run_train_minibatch(h, bt));
+      const SampleArgs sa = make_sample_args(h, seed, (uint32_t)(epoch * cnum + c));
+      TRY(run_train_minibatch(h, bt, &sa));
     }
   }
   return end_call(h, stats);
@@ -728,7 +744,7 @@ int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8
     CU(cudaMemcpyAsync(h->negs.p, negatives, sizeof(int32_t) * (size_t)(slots * h->cfg.num_neg), cudaMemcpyHostToDevice, h->stream));
   h->h2d += (size_t)slots + sizeof(int32_t) * (size_t)(slots * h->cfg.num_neg);
   BatchDev bt = make_batch(h, h->tmp_in.p, n_in, h->tmp_out.p, n_out, h->tmp_uids.p, n);
-  TRY(run_train_minibatch(h, bt));
+  TRY(run_train_minibatch(h, bt, nullptr));
   return end_call(h, stats);
 }
 
@@ -747,7 +763,7 @@ int cdae_encode(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* k
   BatchDev bt = make_batch(h, h->tmp_in.p, n_in, h->tmp_out.p, 0, h->tmp_uids.p, n);
   const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
   CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per, h->stream));
-  TRY(launch_gather(h, bt));
+  TRY(launch_gather(h, bt, nullptr, false));
   TRY(launch_activate(h, bt, (float)scale));
   TRY(ensure(h, h->stage_f, (size_t)(n * h->K)));
   unpack_to_float_kernel<<<cdiv(n * h->K, 256), 256, 0, h->stream>>>(h->stage_f.p, bt.Z, n, h->K, h->ld);
@@ -768,11 +784,11 @@ int cdae_data_loss(cdae_handle* h, uint64_t seed, double* out) {
     for (int c = 0; c < cnum; ++c) {
       BatchDev bt = make_batch(h, h->plan_in.p + p.in0, p.n_in, h->plan_out.p + p.out0, p.n_out,
                                h->plan_uids.p + p.user0, p.n_users);
-      TRY(launch_sample(h, bt, seed, 0x80000000u + (uint32_t)c, false, false));
+      const SampleArgs sa = make_sample_args(h, seed, 0x80000000u + (uint32_t)c);
       CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per, h->stream));
-      TRY(launch_gather(h, bt));
+      TRY(launch_gather(h, bt, &sa, false));
       TRY(launch_activate(h, bt, h->m.scale));
-      TRY(launch_decode(h, bt, false));
+      TRY(launch_decode(h, bt, false, nullptr));
     }
   }
   cdae_epoch_stats_t st;

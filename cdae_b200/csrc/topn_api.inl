@@ -15,7 +15,7 @@ static int encode_all_users(cdae_handle* h) {
     bt.Z = h->topn_z.p + p.uid0 * h->ld;  // a slice's users are consecutive ids
     CU(cudaMemsetAsync(h->keep.p, empty_input ? 0 : 1, (size_t)std::max<int64_t>(p.slots, 1), h->stream));
     CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per, h->stream));
-    TRY(launch_gather(h, bt));
+    TRY(launch_gather(h, bt, nullptr, false));
     TRY(launch_activate(h, bt, 1.f));
   }
   return 0;

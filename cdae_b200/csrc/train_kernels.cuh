@@ -1,18 +1,20 @@
 // cdae_b200/csrc/train_kernels.cuh — the per-user CDAE step as sm_100a kernels.
 //
 // One frozen minibatch of users (SURVEY.md Appendix A "frozen-batch") runs as
-//   sample  -> gather -> activate -> decode -> hidden_backward -> scatter -> apply
-// All item-side tables are row-major [rows][ld] fp32 with ld = round_up(K, 8) (32-byte
-// sectors; pad columns are kept at exactly 0).  A table row is owned by a GROUP of G lanes,
-// each holding NV <= 4 float4 (column 4*(v*G+lane) .. +3): loads are 16 B per lane and
-// contiguous across the group, the K-reduction is a log2(G)-step shuffle, and a warp works on
-// 32/G rows at once, unrolled UNR deep.  G is the SMALLEST power of two with 16*G >= ld
-// (K=50 -> 4 lanes x 4 vectors, 8 rows per warp instruction): the first version used one
-// vector per lane (16 lanes per row at K=50) and ncu showed it issue-bound (59% issue-active,
-// 29% L2 throughput, DRAM idle — profiles/r01_a_*), so the per-row scalar work (ids, loss,
-// shuffles, addressing) is now amortised over 4x more rows per instruction.
+//   gather(+mask) -> activate -> decode(+negatives) -> hidden_backward -> scatter -> apply
 //
-// Reference lines each kernel takes over are cited at the kernel.
+// Layout: all item/user tables are row-major [rows][ld] fp32 with ld = round_up(K, 32): every
+// row is a whole number of 128-byte lines (pad columns are kept at exactly 0).  A row is owned
+// by a GROUP of G >= 8 lanes, each holding NV <= 4 float4 (column 4*(v*G+lane) .. +3), so ONE
+// warp-level 16-byte load/reduction covers whole 128-byte lines of 32/G rows.  History
+// (profiles/r01_*): v1 used 224-byte rows with 16 lanes per row and was issue-bound; v2 used 4
+// lanes per row and was bound by the L1->crossbar REQUEST rate (66% busy, ~10 requests per
+// row because 64-byte pieces of unaligned rows straddle lines); line-aligned rows with 8 lanes
+// need 2 read + 2 reduction requests per row at K=50.
+//
+// Sampling (corruption mask, negatives) is fused into gather / decode: it is pure integer ALU
+// work that overlaps with the memory stalls of those kernels, and the negatives never touch
+// global memory.  Reference lines each kernel takes over are cited at the kernel.
 #pragma once
 #include "common.cuh"
 
@@ -24,7 +26,8 @@ struct ModelDev {
   float *W_ag, *V_ag, *Wu_ag, *b_ag, *bp_ag, *Uu_ag;
   // dense gradient accumulators of one minibatch (one contiguous buffer, all-reduced as one)
   float *gW, *gV, *gbp, *gb;
-  float* g_steps;  // [1] number of user steps that contributed (for the n*lambda*b term)
+  float* g_steps;  // [2] user steps that contributed (n*lambda*b term); slot = minibatch parity
+  int steps_slot;
   int64_t I, U;
   int K, ld;
   float lambda, lr, beta, scale;  // scale = scaled ? 1/(1-q) : 1   (cdae.hpp:202-205)
@@ -33,28 +36,39 @@ struct ModelDev {
 };
 
 struct BatchDev {
-  const WorkItem* in_items;   // input chunks  (<= CH_IN slots each)
+  const WorkItem* in_items;   // input chunks  (<= 64 slots each)
   const WorkItem* out_items;  // output chunks (<= ch_out slots each)
   int n_in_items, n_out_items, n_users;
   const int32_t* uids;        // [n_users] global uid per local row
   const int64_t* row_ptr;     // CSR of the training set (device)
   const int32_t* col;
   uint8_t* keep;              // [minibatch slots]       1 = input item survives corruption
-  int32_t* negs;              // [minibatch slots * nu]  sampled negatives
+  const int32_t* negs;        // [minibatch slots * nu]  explicit negatives (unsampled mode only)
   float *H, *Z, *HG, *D, *GU;  // [n_users][ld]
 };
 
+// Counter-based sampling parameters (same specification as oracle/cdae_oracle.h).
+struct SampleArgs {
+  uint64_t seed;
+  uint32_t pass;       // epoch * num_corruptions + corruption index
+  uint32_t keep_thr;   // floor(q * 2^32)
+  int keep_mode;       // 0 keep all (q <= 0), 1 keep none (q >= 1), 2 Philox
+};
+
+constexpr int STAT_STRIPES = 64;  // same-address atomics serialise in L2: spread them
 struct StatsDev {
-  double loss_sum;
-  unsigned long long outputs, inputs_kept, user_steps;
+  double loss_sum[STAT_STRIPES];
+  unsigned long long outputs[STAT_STRIPES];
+  unsigned long long inputs_kept[STAT_STRIPES];
+  unsigned long long user_steps;
   int bad_loss;  // LOGISTIC fed a score outside (0,1)
   int pad;
 };
 
 template <int G, int NV>
 struct RowMap {
-  static constexpr int NG = 32 / G;         // rows a warp handles at once
-  static constexpr int UNR = G == 1 ? 1 : 2;  // row batches in flight per warp
+  static constexpr int NG = 32 / G;               // rows a warp handles at once
+  static constexpr int UNR = NV <= 2 ? 4 : 2;     // row batches in flight per warp
   __device__ static __forceinline__ int col4(int gl, int v) { return (v * G + gl) * 4; }
 };
 
@@ -98,82 +112,77 @@ __device__ __forceinline__ bool row_contains(const int32_t* row, int n, int item
 }
 
 // ---------------------------------------------------------------------------------------
-// H3 + H5: corruption mask (cdae.hpp:361-371: keep iff uniform > q) and negative sampling
-// (recsys_model_base.hpp:46-57: uniform item, redraw while it is one of the user's positives;
-// n_u*num_neg draws with replacement, cdae.hpp:217-220).  One warp per input chunk.
-__global__ void __launch_bounds__(256) sample_kernel(BatchDev bt, int nu, int64_t I, uint64_t seed,
-                                                     uint32_t pass, uint32_t keep_thr,
-                                                     int keep_mode /*0 all,1 none,2 philox*/,
-                                                     StatsDev* stats) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  WorkItem wi = load_item(bt.in_items + min(warp, bt.n_in_items - 1));
-  if (warp >= bt.n_in_items) wi.n = 0;  // keep the whole block alive for the block reduction
-  const int64_t r0 = __ldg(bt.row_ptr + wi.uid);
-  const int n_u = (int)(__ldg(bt.row_ptr + wi.uid + 1) - r0);
-  const int32_t* row = bt.col + r0;
+// H3, cdae.hpp:361-371: an input item is kept iff uniform > q.  Slot s of the user's row takes
+// word (s&3) of philox({uid, s>>2, pass, 0}); chunks start at multiples of 64 slots, so slots
+// 4q..4q+3 of a chunk share one call.  Warp-cooperative; returns this lane's kept count.
+__device__ __forceinline__ int sample_keep_chunk(const WorkItem& wi, const SampleArgs& sa,
+                                                 uint8_t* keep, int lane) {
   int kept = 0;
-  // chunks start at multiples of 64 slots, so slots 4q..4q+3 of the chunk share one Philox call
   for (int q = lane; q * 4 < wi.n; q += 32) {
     Philox4 p = {0u, 0u, 0u, 0u};
-    if (keep_mode == 2) p = philox4x32(seed, (uint32_t)wi.uid, (uint32_t)((wi.row_off >> 2) + q), pass, 0u);
-    for (int i = q * 4; i < min(q * 4 + 4, wi.n); ++i) {
+    if (sa.keep_mode == 2)
+      p = philox4x32(sa.seed, (uint32_t)wi.uid, (uint32_t)((wi.row_off >> 2) + q), sa.pass, 0u);
+    const int lim = min(4, wi.n - q * 4);
+    for (int i = 0; i < lim; ++i) {
       uint8_t k;
-      if (keep_mode == 0) k = 1;
-      else if (keep_mode == 1) k = 0;
-      else k = philox_word(p, i & 3) > keep_thr;  // cdae.hpp:366: keep iff uniform > ratio
-      bt.keep[wi.aux0 + i] = k;
-      kept += k;
+      if (sa.keep_mode == 0) k = 1;
+      else if (sa.keep_mode == 1) k = 0;
+      else k = philox_word(p, i) > sa.keep_thr;
+      keep[q * 4 + i] = k;
+      kept += (int)k;
     }
   }
-  // Negatives: draw d of the user takes word (d&3) of philox({uid, d>>2, pass, 1}) — one Philox
-  // call serves four draws — and, only if that item is one of the user's positives (probability
-  // n_u/I), retries a = 1,2,.. from word ((a-1)&3) of philox({uid, d, pass, 2 + ((a-1)>>2)}).
-  // Chunks start at multiples of 64 slots, so a lane's quad of draws never straddles a call.
+  return kept;
+}
+
+// H5, recsys_model_base.hpp:46-57 + cdae.hpp:217-220: n_u*num_neg draws with replacement,
+// uniform over items, redrawn while the item is one of the user's positives.  Draw d of the user
+// takes word (d&3) of philox({uid, d>>2, pass, 1}) — one call serves four draws — and, only if
+// that item is a positive (probability n_u/I), retries a = 1,2,.. from word ((a-1)&3) of
+// philox({uid, d, pass, 2 + ((a-1)>>2)}).  Warp-cooperative: fills out[0 .. n*nu).
+__device__ __forceinline__ void sample_negs_chunk(const WorkItem& wi, const SampleArgs& sa, int nu,
+                                                  int64_t I, const int64_t* row_ptr,
+                                                  const int32_t* col, int32_t* out, int lane) {
   const int ndraw = wi.n * nu;
-  int32_t* out = bt.negs + (int64_t)wi.aux0 * nu;
+  if (ndraw == 0) return;
+  const int64_t r0 = __ldg(row_ptr + wi.uid);
+  const int n_u = (int)(__ldg(row_ptr + wi.uid + 1) - r0);
+  const int32_t* row = col + r0;
   const uint32_t d_base = (uint32_t)(wi.row_off * nu);
-  const uint32_t d_head = (4u - (d_base & 3u)) & 3u;  // draws before the first aligned quad
-  const int nquad = ((int)d_head > 0 ? 1 : 0) + (ndraw - min((int)d_head, ndraw) + 3) / 4;
+  const int d_head = (int)((4u - (d_base & 3u)) & 3u);  // draws before the first aligned quad
+  const int nquad = (d_head > 0 ? 1 : 0) + (ndraw - min(d_head, ndraw) + 3) / 4;
   for (int q = lane; q < nquad; q += 32) {
     int j0, j1;  // [j0, j1) = this quad's draws inside the chunk
     if (d_head > 0) {
-      j0 = q == 0 ? 0 : (int)d_head + (q - 1) * 4;
-      j1 = q == 0 ? (int)d_head : j0 + 4;
+      j0 = q == 0 ? 0 : d_head + (q - 1) * 4;
+      j1 = q == 0 ? d_head : j0 + 4;
     } else {
       j0 = q * 4;
       j1 = j0 + 4;
     }
     j1 = min(j1, ndraw);
     if (j0 >= j1) continue;
-    const Philox4 p0 = philox4x32(seed, (uint32_t)wi.uid, (d_base + (uint32_t)j0) >> 2, pass, 1u);
+    const Philox4 p0 = philox4x32(sa.seed, (uint32_t)wi.uid, (d_base + (uint32_t)j0) >> 2, sa.pass, 1u);
     for (int j = j0; j < j1; ++j) {
       const uint32_t d = d_base + (uint32_t)j;
       int32_t item = (int32_t)(((uint64_t)philox_word(p0, d & 3) * (uint64_t)I) >> 32);
       for (uint32_t a = 1; row_contains(row, n_u, item); ++a) {
-        const Philox4 p = philox4x32(seed, (uint32_t)wi.uid, d, pass, 2u + ((a - 1) >> 2));
+        const Philox4 p = philox4x32(sa.seed, (uint32_t)wi.uid, d, sa.pass, 2u + ((a - 1) >> 2));
         item = (int32_t)(((uint64_t)philox_word(p, (a - 1) & 3) * (uint64_t)I) >> 32);
       }
       out[j] = item;
     }
   }
-  if (stats) {  // one atomic per block, not per warp (same-address atomics serialise in L2)
-    __shared__ int kept_s;
-    if (threadIdx.x == 0) kept_s = 0;
-    __syncthreads();
-    kept = (int)group_sum<32>((float)kept);
-    if (lane == 0) atomicAdd(&kept_s, kept);
-    __syncthreads();
-    if (threadIdx.x == 0 && kept_s) atomicAdd(&stats->inputs_kept, (unsigned long long)kept_s);
-  }
 }
 
 // ---------------------------------------------------------------------------------------
-// H4 first half, cdae.hpp:375-380: H[u] += sum over kept inputs of W[item]  (the scale factor
-// is applied in activate_kernel).  One warp per input chunk; chunks of one user add up with
-// 16-byte reductions (H is zeroed per minibatch).
-template <int G, int NV>
-__global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt) {
+// H3 + H4 first half, cdae.hpp:361-380: (SAMPLED: draw the chunk's corruption mask, store it for
+// decode / scatter) then H[u] += sum over kept inputs of W[item]  (the scale factor is applied in
+// activate_kernel).  One warp per input chunk; chunks of one user add up with 16-byte
+// reductions (H is zeroed per minibatch).
+template <int G, int NV, bool SAMPLED>
+__global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, SampleArgs sa,
+                                                     StatsDev* stats) {
   using RM = RowMap<G, NV>;
   constexpr int NG = RM::NG, UNR = RM::UNR;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -181,7 +190,14 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt) {
   const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
   const WorkItem wi = load_item(bt.in_items + warp);
   const int32_t* items = bt.col + wi.s0;
-  const uint8_t* keep = bt.keep + wi.aux0;
+  uint8_t* keep = bt.keep + wi.aux0;
+  if (SAMPLED) {
+    int kept = sample_keep_chunk(wi, sa, keep, lane);
+    kept = (int)group_sum<32>((float)kept);
+    if (lane == 0 && stats && kept)
+      atomicAdd(&stats->inputs_kept[warp % STAT_STRIPES], (unsigned long long)kept);
+    __syncwarp();  // the mask bytes written above are read by other lanes below
+  }
   float4 acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = f4zero();
@@ -234,30 +250,33 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
 }
 
 // ---------------------------------------------------------------------------------------
-// H6 + H7, cdae.hpp:225-293 (+ get_output_values :418-426, Loss::gradient): for every output
-// o of the chunk (its positives, then their negatives): y = W'[o].z + b'[o]; g = l'(y,t);
-// hg += g*W'[o]; gW'[o] += g*z + lambda*W'[o]; gb'[o] += g + lambda*b'[o].
+// H5 + H6 + H7, cdae.hpp:217-293 (+ get_output_values :418-426, Loss::gradient): (SAMPLED: draw
+// the chunk's negatives into shared memory) then for every output o of the chunk (its positives,
+// then their negatives): y = W'[o].z + b'[o]; g = l'(y,t); hg += g*W'[o];
+// gW'[o] += g*z + lambda*W'[o]; gb'[o] += g + lambda*b'[o].
 // Tied weights and o in the corrupted input: the lambda term is left to scatter_kernel so the
 // row receives ONE lambda per merged occurrence (cdae.hpp:249-250, 342-343).
 // TRAIN=false scores the positives only and accumulates loss(y,1): CDAE::data_loss :93-96.
-template <int G, int NV, bool TRAIN>
-__global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, StatsDev* stats) {
+constexpr int DECODE_MAX_NEGS = 96;  // ch_out * num_neg <= 96 by construction (api.cu)
+template <int G, int NV, bool TRAIN, bool SAMPLED>
+__global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, SampleArgs sa,
+                                                     StatsDev* stats) {
   using RM = RowMap<G, NV>;
   constexpr int NG = RM::NG, UNR = RM::UNR;
-  __shared__ float blk_loss;
-  __shared__ int blk_out;
-  if (threadIdx.x == 0) {
-    blk_loss = 0.f;
-    blk_out = 0;
-  }
-  __syncthreads();
+  __shared__ int32_t negs_s[SAMPLED && TRAIN ? 8 : 1][SAMPLED && TRAIN ? DECODE_MAX_NEGS : 1];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= bt.n_out_items) return;
   const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
-  WorkItem wi = load_item(bt.out_items + min(warp, bt.n_out_items - 1));
-  if (warp >= bt.n_out_items) wi.n = 0;  // idle warp of the last block: no rows, joins the barrier
+  const WorkItem wi = load_item(bt.out_items + warp);
   const int32_t* pos = bt.col + wi.s0;
   const uint8_t* keep = bt.keep + wi.aux0;
   const int32_t* neg = bt.negs + (int64_t)wi.aux0 * m.nu;
+  if (SAMPLED && TRAIN) {
+    int32_t* mine = negs_s[threadIdx.x >> 5];
+    sample_negs_chunk(wi, sa, m.nu, m.I, bt.row_ptr, bt.col, mine, lane);
+    __syncwarp();
+    neg = mine;
+  }
   const float* Wd = m.asym ? m.V : m.W;
   float* gWd = m.asym ? m.gV : m.gW;
   const int n = wi.n;
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, St
         it[t] = __ldg(pos + r);
         merged[t] = TRAIN && tied && keep[r];
       } else if (r < R) {
-        it[t] = __ldg(neg + (r - n));
+        it[t] = neg[r - n];
       }
     }
     float4 w[UNR][NV];
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, St
       if (gl == 0) red_add_f32(m.gbp + it[t], g + m.lambda * bp[t]);
     }
   }
-  if (TRAIN && wi.n > 0) {
+  if (TRAIN) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       hg[v] = cross_group_sum<G>(hg[v]);
@@ -341,15 +360,10 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, St
   }
   loss_acc = group_sum<32>(loss_acc);
   bad = __any_sync(0xffffffffu, bad);
-  if (lane == 0) {  // block-level partials first: same-address global atomics serialise in L2
-    atomicAdd(&blk_loss, loss_acc);
-    atomicAdd(&blk_out, R);
+  if (lane == 0) {
+    atomicAdd(&stats->loss_sum[warp % STAT_STRIPES], (double)loss_acc);
+    atomicAdd(&stats->outputs[warp % STAT_STRIPES], (unsigned long long)R);
     if (bad) stats->bad_loss = 1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicAdd(&stats->loss_sum, (double)blk_loss);
-    atomicAdd(&stats->outputs, (unsigned long long)blk_out);
   }
 }
 
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchD
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int cnt = min((int)blockDim.y, bt.n_users - blockIdx.x * (int)blockDim.y);
     if (cnt > 0) {
-      red_add_f32(m.g_steps, (float)cnt);
+      red_add_f32(m.g_steps + m.steps_slot, (float)cnt);
       atomicAdd(&stats->user_steps, (unsigned long long)cnt);
     }
   }
@@ -507,10 +521,12 @@ struct ApplyArgs {
   int nseg;
   float lr, beta;
   int adagrad;
-  const float* g_steps;
+  float* g_steps;  // [2]: read slot `steps_slot`, clear the other one for the next minibatch
+  int steps_slot;
 };
 __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
-  const float steps = *a.g_steps;
+  const float steps = a.g_steps[a.steps_slot];
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.g_steps[a.steps_slot ^ 1] = 0.f;
   for (int s = 0; s < a.nseg; ++s) {
     const ApplySeg sg = a.seg[s];
     const float extra = sg.extra_coef * steps;
