@@ -52,6 +52,7 @@ SIGNATURES = {
     "cdae_param_shape": (C.c_int, [C.c_void_p, C.c_int, i64p, i64p]),
     "cdae_set_param": (C.c_int, [C.c_void_p, C.c_int, f64p, C.c_int64]),
     "cdae_get_param": (C.c_int, [C.c_void_p, C.c_int, f64p, C.c_int64]),
+    "cdae_get_param_rows": (C.c_int, [C.c_void_p, C.c_int, i64p, C.c_int64, f64p]),
     "cdae_train_epoch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(EpochStats)]),
     "cdae_train_epoch_csr": (C.c_int, [C.c_void_p, i64p, i32p, C.c_uint64, C.c_int64,
                                        C.POINTER(EpochStats)]),

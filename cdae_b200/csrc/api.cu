@@ -652,6 +652,38 @@ int cdae_get_param(cdae_handle* h, int which, double* dst, int64_t n) {
   return 0;
 }
 
+// selected rows of a table (or selected entries of b') as doubles
+__global__ void gather_rows_to_double_kernel(double* dst, const float* src, const int64_t* rows,
+                                             int64_t n, int K, int ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * K) return;
+  dst[i] = (double)src[rows[i / K] * ld + (i % K)];
+}
+
+int cdae_get_param_rows(cdae_handle* h, int which, const int64_t* rows, int64_t n, double* dst) {
+  if (!h || !rows || !dst || n <= 0) return set_error(CDAE_E_INVALID, "NULL / empty argument");
+  CU(cudaSetDevice(h->cfg.device));
+  int64_t r, c; int ld;
+  float* p = param_ptr(h, which, &r, &c, &ld);
+  if (which < 0 || which >= CDAE_P_COUNT || !p || r * c == 0) return set_error(CDAE_E_INVALID, "parameter block %d is absent", which);
+  const bool vec = which == CDAE_P_B || which == CDAE_P_B_AG || which == CDAE_P_BPRIME || which == CDAE_P_BPRIME_AG;
+  const bool user_block = which == CDAE_P_WU || which == CDAE_P_WU_AG || which == CDAE_P_UU || which == CDAE_P_UU_AG;
+  if (h->world > 1 && user_block) return set_error(CDAE_E_STATE, "row reads of user-private blocks are single-process; use cdae_get_param");
+  const int64_t limit = vec ? c : r;   // vectors: `rows` index the entries
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= limit) return set_error(CDAE_E_INVALID, "row %lld outside [0,%lld)", (long long)rows[i], (long long)limit);
+  const int K = vec ? 1 : (int)c, L = vec ? 1 : ld;
+  // staging: [n*K doubles | n int64 row ids]
+  TRY(ensure(h, h->stage_d, (size_t)(n * K + n)));
+  int64_t* rows_d = reinterpret_cast<int64_t*>(h->stage_d.p + n * K);
+  CU(cudaMemcpyAsync(rows_d, rows, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
+  gather_rows_to_double_kernel<<<cdiv(n * K, 256), 256, 0, h->stream>>>(h->stage_d.p, p, rows_d, n, K, L);
+  KERNEL_OK(h);
+  CU(cudaMemcpyAsync(dst, h->stage_d.p, sizeof(double) * n * K, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats) {
   if (!h->plan_valid) TRY(build_plan(h));
   TRY(ensure_scratch(h, h->plan_max_users, h->plan_max_slots));

@@ -12,6 +12,8 @@
 #ifndef CDAE_B200_COMPAT_BOOST_ARCHIVE_DETAIL_HPP_
 #define CDAE_B200_COMPAT_BOOST_ARCHIVE_DETAIL_HPP_
 
+#include "../../std_prelude.h"
+
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>

@@ -5,6 +5,8 @@
 #ifndef CDAE_B200_COMPAT_BOOST_IOSTREAMS_FILTERING_STREAM_HPP_
 #define CDAE_B200_COMPAT_BOOST_IOSTREAMS_FILTERING_STREAM_HPP_
 
+#include "../../std_prelude.h"
+
 #include <cstdlib>
 #include <iostream>
 #include <sstream>

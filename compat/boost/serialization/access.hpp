@@ -3,6 +3,7 @@
 // T::serialize(ar, version) through this class.
 #ifndef CDAE_B200_COMPAT_BOOST_SERIALIZATION_ACCESS_HPP_
 #define CDAE_B200_COMPAT_BOOST_SERIALIZATION_ACCESS_HPP_
+#include <type_traits>
 namespace boost {
 namespace serialization {
 class access {
@@ -20,12 +21,19 @@ class access {
     t.load(ar, version);
   }
 };
+// Tag dispatch on Archive::is_saving so only the matching half is instantiated (the save half
+// streams const members, which an input archive cannot bind).
+template <class Archive, class T>
+inline void split_member_impl(Archive& ar, T& t, const unsigned int version, std::true_type) {
+  access::member_save(ar, t, version);
+}
+template <class Archive, class T>
+inline void split_member_impl(Archive& ar, T& t, const unsigned int version, std::false_type) {
+  access::member_load(ar, t, version);
+}
 template <class Archive, class T>
 inline void split_member(Archive& ar, T& t, const unsigned int version) {
-  if (Archive::is_saving::value)
-    access::member_save(ar, t, version);
-  else
-    access::member_load(ar, t, version);
+  split_member_impl(ar, t, version, typename Archive::is_saving());
 }
 template <class T>
 struct array_wrapper {

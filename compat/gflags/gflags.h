@@ -7,6 +7,8 @@
 #ifndef CDAE_B200_COMPAT_GFLAGS_GFLAGS_H_
 #define CDAE_B200_COMPAT_GFLAGS_GFLAGS_H_
 
+#include "../std_prelude.h"
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>

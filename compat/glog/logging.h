@@ -11,6 +11,8 @@
 #ifndef CDAE_B200_COMPAT_GLOG_LOGGING_H_
 #define CDAE_B200_COMPAT_GLOG_LOGGING_H_
 
+#include "../std_prelude.h"
+
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>

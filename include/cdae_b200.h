@@ -122,6 +122,9 @@ int cdae_init_params(cdae_handle* h, uint64_t seed);
 int cdae_param_shape(cdae_handle* h, int which, int64_t* rows, int64_t* cols);
 int cdae_set_param(cdae_handle* h, int which, const double* src, int64_t n);
 int cdae_get_param(cdae_handle* h, int which, double* dst, int64_t n);
+/* n selected rows of a table (dst: n x K doubles) or n selected entries of b / b' (dst: n
+ * doubles) — what CDAE::get_output_values (cdae.hpp:418-426) reads: W'.row(i) and b'(i). */
+int cdae_get_param_rows(cdae_handle* h, int which, const int64_t* rows, int64_t n, double* dst);
 
 /* CDAE::train_one_iteration (cdae.hpp:136-146): one pass over users [0,U) in minibatches of
  * batch_users, masks and negatives from Philox(seed, epoch) (spec in DESIGN.md; identical

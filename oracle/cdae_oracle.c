@@ -400,9 +400,12 @@ static void touch(int64_t** list, int64_t* n, int64_t* cap, char* flag, int64_t 
   (*list)[(*n)++] = r;
 }
 
-void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
-                     const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
-                     double* loss_sum_out) {
+/* ext == NULL: the frozen-batch step.  ext != NULL (data-parallel shard): the item-side
+ * gradients are ADDED to ext = [gW (I*K) | gV (I*K, asymmetric only) | gb' (I) | gb (K)] instead
+ * of being applied; only the user-private rows (Wu, Uu) are updated here. */
+static void step_frozen_impl(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                             const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
+                             double* loss_sum_out, double* ext) {
   const int K = m->K;
   const orc_config* c = &m->cfg;
   const int64_t I = m->I;
@@ -486,6 +489,19 @@ void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids, const i
       touch(&ws.touchW, &ws.nW, &ws.capW, ws.flagW, in[j]);
     }
   }
+  if (ext) {
+    double* e = ext;
+    for (int64_t i = 0; i < I * K; ++i) e[i] += ws.gW[i];
+    e += I * K;
+    if (c->asymmetric) {
+      for (int64_t i = 0; i < I * K; ++i) e[i] += ws.gV[i];
+      e += I * K;
+    }
+    for (int64_t i = 0; i < I; ++i) e[i] += ws.gbp[i];
+    e += I;
+    for (int k = 0; k < K; ++k) e[k] += ws.gb[k];
+    ws.nW = ws.nV = ws.nbp = 0; /* nothing item-side is applied below */
+  }
   /* one upd per touched row */
   for (int64_t t = 0; t < ws.nW; ++t) {
     int64_t r = ws.touchW[t];
@@ -499,7 +515,7 @@ void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids, const i
     int64_t r = ws.touchbp[t];
     upd_scalar(m, &m->p[ORC_BPRIME][r], &m->p[ORC_BPRIME_AG][r], ws.gbp[r]);
   }
-  if (n_users > 0) upd_row(m, m->p[ORC_B], m->p[ORC_B_AG], ws.gb, K);
+  if (n_users > 0 && !ext) upd_row(m, m->p[ORC_B], m->p[ORC_B_AG], ws.gb, K);
   for (int64_t ui = 0; ui < n_users; ++ui) {
     if (c->user_factor)
       upd_row(m, m->p[ORC_WU] + uids[ui] * K, m->p[ORC_WU_AG] + uids[ui] * K, gWu + ui * K, K);
@@ -511,6 +527,49 @@ void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids, const i
   free(ws.flagW); free(ws.flagV); free(ws.flagbp);
   free(ws.touchW); free(ws.touchV); free(ws.touchbp);
   free(gWu); free(gUu); free(z);
+}
+
+void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                     const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
+                     double* loss_sum_out) {
+  step_frozen_impl(m, n_users, uids, in_ptr, in_items, neg_ptr, negs, loss_sum_out, NULL);
+}
+
+void orc_shard_gradients(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                         const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
+                         double* loss_sum_out, double* dense_grad) {
+  step_frozen_impl(m, n_users, uids, in_ptr, in_items, neg_ptr, negs, loss_sum_out, dense_grad);
+}
+
+/* One upd per element whose summed gradient is non-zero (upd with g = 0 is a no-op, so this
+ * equals "one upd per touched row"); any_steps = 0 skips b (no user contributed). */
+void orc_apply_dense(orc_model* m, const double* dense_grad, int any_steps) {
+  const int K = m->K;
+  const int64_t I = m->I;
+  const double* e = dense_grad;
+  double* g = (double*)malloc(sizeof(double) * (size_t)K);
+  for (int64_t r = 0; r < I; ++r) {
+    int nz = 0;
+    for (int k = 0; k < K; ++k) { g[k] = e[r * K + k]; nz |= g[k] != 0.; }
+    if (nz) upd_row(m, m->p[ORC_W] + r * K, m->p[ORC_W_AG] + r * K, g, K);
+  }
+  e += I * K;
+  if (m->cfg.asymmetric) {
+    for (int64_t r = 0; r < I; ++r) {
+      int nz = 0;
+      for (int k = 0; k < K; ++k) { g[k] = e[r * K + k]; nz |= g[k] != 0.; }
+      if (nz) upd_row(m, m->p[ORC_V] + r * K, m->p[ORC_V_AG] + r * K, g, K);
+    }
+    e += I * K;
+  }
+  for (int64_t r = 0; r < I; ++r)
+    if (e[r] != 0.) upd_scalar(m, &m->p[ORC_BPRIME][r], &m->p[ORC_BPRIME_AG][r], e[r]);
+  e += I;
+  if (any_steps) {
+    for (int k = 0; k < K; ++k) g[k] = e[k];
+    upd_row(m, m->p[ORC_B], m->p[ORC_B_AG], g, K);
+  }
+  free(g);
 }
 
 /* ------------------------------------------------------------------ recommend */

@@ -77,6 +77,17 @@ void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids,
                      const int64_t* in_ptr, const int64_t* in_items,
                      const int64_t* neg_ptr, const int64_t* negs, double* loss_sum_out);
 
+/* Data-parallel decomposition of the frozen-batch step (what each GPU rank computes, SURVEY.md
+ * §8e): orc_shard_gradients evaluates a SHARD of a minibatch at the frozen parameters, ADDS its
+ * item-side gradients to dense_grad = [gW (I*K) | gV (I*K, asymmetric only) | gb' (I) | gb (K)]
+ * and updates only the shard's user-private rows (Wu, Uu); orc_apply_dense applies the summed
+ * gradient once.  shard_gradients over all shards + apply_dense == orc_step_frozen. */
+void orc_shard_gradients(orc_model* m, int64_t n_users, const int64_t* uids,
+                         const int64_t* in_ptr, const int64_t* in_items,
+                         const int64_t* neg_ptr, const int64_t* negs, double* loss_sum_out,
+                         double* dense_grad);
+void orc_apply_dense(orc_model* m, const double* dense_grad, int any_steps);
+
 /* cdae.hpp:162-196 with rated = the user's train row.  ids sorted by score desc
  * (exact-score ties: lower id first; the reference leaves tie order unspecified). */
 int orc_recommend(const orc_model* m, int64_t uid, int64_t topk, int64_t* ids_out,

@@ -89,6 +89,9 @@ def _orc():
         L.orc_step_sequential.argtypes = [C.c_void_p, C.c_int64, i64p, C.c_int64, i64p, C.c_int64,
                                           i64p]
         L.orc_step_frozen.argtypes = [C.c_void_p, C.c_int64, i64p, i64p, i64p, i64p, i64p, f64p]
+        L.orc_shard_gradients.argtypes = [C.c_void_p, C.c_int64, i64p, i64p, i64p, i64p, i64p, f64p,
+                                          f64p]
+        L.orc_apply_dense.argtypes = [C.c_void_p, f64p, C.c_int]
         L.orc_recommend.restype = C.c_int
         L.orc_recommend.argtypes = [C.c_void_p, C.c_int64, C.c_int64, i64p, f64p]
         L.orc_data_loss.restype = C.c_double
@@ -206,6 +209,31 @@ class Oracle:
         self._L.orc_step_frozen(self._h, len(uids), _p(uids, i64p), _p(in_ptr, i64p),
                                 _p(ins, i64p), _p(neg_ptr, i64p), _p(ngs, i64p), C.byref(ls))
         return ls.value
+
+    def dense_grad_size(self):
+        """[gW | gV (asymmetric) | gb' | gb] — the buffer the GPU path all-reduces."""
+        K = self.cfg["num_dim"]
+        return self.I * K * (2 if self.cfg["asymmetric"] else 1) + self.I + K
+
+    def shard_gradients(self, uids, in_lists, neg_lists, dense):
+        """Frozen-parameter gradients of a minibatch SHARD: item side added to `dense`,
+        user-private rows updated in place.  Returns the shard's loss sum."""
+        uids = _as(uids, np.int64)
+        in_ptr = np.zeros(len(uids) + 1, np.int64)
+        neg_ptr = np.zeros(len(uids) + 1, np.int64)
+        in_ptr[1:] = np.cumsum([len(x) for x in in_lists])
+        neg_ptr[1:] = np.cumsum([len(x) for x in neg_lists])
+        ins = _as(np.concatenate([np.asarray(x, np.int64) for x in in_lists] + [np.zeros(0, np.int64)]), np.int64)
+        ngs = _as(np.concatenate([np.asarray(x, np.int64) for x in neg_lists] + [np.zeros(0, np.int64)]), np.int64)
+        assert dense.dtype == np.float64 and dense.flags.c_contiguous and dense.size == self.dense_grad_size()
+        ls = C.c_double(0)
+        self._L.orc_shard_gradients(self._h, len(uids), _p(uids, i64p), _p(in_ptr, i64p),
+                                    _p(ins, i64p), _p(neg_ptr, i64p), _p(ngs, i64p), C.byref(ls),
+                                    _p(dense, f64p))
+        return ls.value
+
+    def apply_dense(self, dense, any_steps=True):
+        self._L.orc_apply_dense(self._h, _p(dense, f64p), int(any_steps))
 
     def recommend(self, uid, topk=10):
         ids = np.zeros(topk, np.int64)

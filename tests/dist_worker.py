@@ -1,0 +1,106 @@
+"""Multi-GPU parity worker: launched by tests/test_gpu_dist.py under torchrun (one process per GPU).
+
+Every rank trains the same problem data-parallel (users of each minibatch sharded over ranks, ONE
+NCCL all-reduce of the dense item-side gradients per minibatch) and rank 0
+compares the result with the CPU oracle's frozen-batch epoch on the SAME global minibatches:
+the set of per-user gradients does not depend on the GPU count, only the fp32 summation order.
+Also checks data_loss (sum of per-rank partials) and the per-rank top-N tables.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from cdae_b200 import CDAE, CDAEConfig
+    from cdae_b200.dist import owned_users
+    from oracle import oracle as orc
+    from tests import cases
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    failures = []
+    try:
+        _run(rank, world, local, failures)
+    except Exception as e:  # noqa: BLE001 - report, then still join the final collective
+        import traceback
+        print("[rank %d] FAIL exception: %r\n%s" % (rank, e, traceback.format_exc()), flush=True)
+        os._exit(3)          # peers are blocked inside NCCL: die loudly, torchrun tears the group down
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    for f in failures:
+        print("[rank %d] FAIL %s" % (rank, f), flush=True)
+    if rank == 0:
+        print("dist_worker: world=%d %s" % (world, "ok" if flag.item() == 0 else "FAILED"), flush=True)
+    dist.destroy_process_group()
+    return 1 if flag.item() else 0
+
+
+def _run(rank, world, local, failures):
+    import torch.distributed as dist
+    from cdae_b200 import CDAE, CDAEConfig
+    from cdae_b200.dist import owned_users
+    from oracle import oracle as orc
+    from tests import cases
+    for kw in (dict(loss="CE", beta=1.0, num_dim=50), dict(loss="SQUARE", asymmetric=True, num_dim=20),
+               dict(loss="CE", user_factor=False, num_dim=33)):
+        cfg = orc.default_config(**kw)
+        data = cases.small_dataset(U=403, I=500, mean=12.0, seed=5)
+        U, I, K = data["U"], data["I"], cfg["num_dim"]
+        rp, col = data["train_row_ptr"], data["train_col"]
+        p = cases.random_params(U, I, K, 9, cfg["asymmetric"], cfg["user_factor"])
+        B = 96                                            # global minibatch (not a multiple of world)
+        m = CDAE(CDAEConfig(batch_users=B, device=local, **cfg)).reset(U, I, rp, col)
+        uid = [CDAE.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        m.dist_init(rank, world, uid[0])
+        m.set_params(p)
+        steps = 0
+        for epoch in range(2):
+            st = m.train_one_iteration(seed=123, epoch=epoch)
+            steps += st.user_steps
+        mine = owned_users(U, B, rank, world)
+        if steps != 2 * len(mine):
+            failures.append("rank %d trained %d user steps, owns %d users" % (rank, steps, len(mine)))
+        got = {k: m.get_param(k) for k in ("W", "V", "Wu", "b", "b_prime", "W_ag", "Wu_ag", "b_ag")}
+        loss = m.data_loss(seed=7)
+        ids, _ = m.recommend_all(10)
+        if rank == 0:
+            o = orc.Oracle(cfg, U, I, rp, col)
+            o.set_params(p)
+            for epoch in range(2):
+                o.train_epoch(123, epoch, batch_users=B)
+            for k, v in got.items():
+                ref = o.param(k)
+                if ref.size == 0 or v.size == 0:
+                    continue
+                err = np.abs(v - ref).max() / max(1e-12, np.abs(ref).max())
+                if not err <= 2e-4:
+                    failures.append("%s %s: max err %.3g" % (kw, k, err))
+            keep = np.concatenate([o.sample_keep(7, 0x80000000, u) for u in range(U)])
+            ref_loss = o.data_loss(keep)
+            if not abs(loss - ref_loss) <= 2e-4 * abs(ref_loss):
+                failures.append("%s data_loss %.6f vs %.6f" % (kw, loss, ref_loss))
+        # every rank: its own users' lists match the oracle evaluated on ITS (identical) parameters
+        o2 = orc.Oracle(cfg, U, I, rp, col)
+        o2.set_params({k: v for k, v in m.get_params().items() if v.size})
+        for u in mine[:: max(1, len(mine) // 40)]:
+            if ids[u].tolist() != o2.recommend(int(u), 10)[0].tolist():
+                failures.append("%s rank %d user %d top-10 differs" % (kw, rank, u))
+                break
+        m.close()
+
+
+if __name__ == "__main__":
+    sys.exit(main())
