@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + SOURCES + ["-o", SO, "-ldl", "-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + SOURCES + ["-o", SO, "-ldl"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

@@ -15,6 +15,7 @@
 #include "../../include/cdae_b200.h"
 #include "handle.cuh"
 #include "topn_kernels.cuh"
+#include "topn_tc.cuh"
 #include "train_kernels.cuh"
 
 using namespace cdae;
@@ -568,6 +569,8 @@ int cdae_destroy(cdae_handle* h) {
   h->topn_ids.release(); h->topn_scores.release(); h->topn_z.release();
   h->cand_id.release(); h->cand_cnt.release(); h->cand_s.release(); h->flag_d.release();
   h->test_rp_d.release(); h->test_col_d.release();
+  h->tc_zb.release(); h->tc_wb.release(); h->tc_wmax.release(); h->tc_eps.release();
+  h->tc_thr.release(); h->tc_redo.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);
   if (h->ev0) cudaEventDestroy(h->ev0);

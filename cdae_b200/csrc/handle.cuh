@@ -85,6 +85,12 @@ struct cdae_handle {
   cdae::DevBuf<float> topn_z;         // [U][ld] uncorrupted hidden vectors
   cdae::DevBuf<int> cand_id, cand_cnt, flag_d;
   cdae::DevBuf<float> cand_s;
+  // tensor-core candidate path (topn_tc.cuh)
+  cdae::DevBuf<uint16_t> tc_zb, tc_wb;   // bf16 operands [rows_pad][Kp]
+  cdae::DevBuf<float> tc_wmax, tc_eps, tc_thr;
+  cdae::DevBuf<int32_t> tc_redo;         // [n_users] + 1 counter at the end
+  int64_t topn_tc_users = 0, topn_redo_users = 0;  // last cdae_topn_build: verified on the tensor path / redone exactly
+  int topn_path = 0;                     // 0 fp32 CUDA cores, 1 tcgen05
   cdae::DevBuf<int64_t> test_rp_d;
   cdae::DevBuf<int32_t> test_col_d;
   std::vector<int32_t> topn_ids_h;    // host mirror for thread-safe lookups

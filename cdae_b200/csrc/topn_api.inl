@@ -21,6 +21,109 @@ static int encode_all_users(cdae_handle* h) {
   return 0;
 }
 
+// ---- tensor-core candidate phase (topn_tc.cuh) ---------------------------------------------
+static int tc_make_map(CUtensorMap* m, void* base, uint64_t rows, uint64_t Kp, uint32_t box_rows) {
+  cuuint64_t dims[2] = {Kp, rows};
+  cuuint64_t strides[1] = {Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tc::KBLK, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  // the driver entry point is fetched through the runtime so the library has no link-time
+  // dependency on libcuda.so.1 (it must load, for symbol checks, on machines without a driver)
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return set_error(CDAE_E_CUDA, "driver lacks cuTensorMapEncodeTiled");
+    encode = (encode_fn)fn;
+  }
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(CDAE_E_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+  return 0;
+}
+
+static bool tc_path_wanted(cdae_handle* h, int topk) {
+  const char* e = getenv("CDAE_B200_TOPN");  // "fp32" forces the CUDA-core path, "tc" is the default
+  if (e && strcmp(e, "fp32") == 0) return false;
+  return h->K + 2 <= tc::MAX_KB * tc::KBLK && topk <= 16;
+}
+
+template <int KB>
+static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const tc::TcArgs& a, int grid) {
+  static bool attr_set = false;
+  const size_t dyn = tc::smem_bytes(KB);
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(tc::topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  tc::topn_tc_kernel<KB><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
+  return 0;
+}
+
+// Candidates + verified exact lists for the users the bound proves; *n_redo users are left in
+// h->tc_redo for the exact path.
+static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users,
+                              int topk, int* n_redo) {
+  const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
+  const int64_t n_pad = round_up(n_users, tc::TILE_U), I_pad = round_up(h->I, tc::TILE_I);
+  TRY(ensure(h, h->tc_zb, (size_t)(n_pad * Kp)));
+  TRY(ensure(h, h->tc_wb, (size_t)(I_pad * Kp)));
+  TRY(ensure(h, h->tc_wmax, (size_t)round_up(K + 1, 4)));
+  TRY(ensure(h, h->tc_eps, (size_t)n_users));
+  TRY(ensure(h, h->tc_thr, (size_t)n_users));
+  TRY(ensure(h, h->tc_redo, (size_t)n_users + 1));
+  int* redo_cnt = h->tc_redo.p + n_users;
+  CU(cudaMemsetAsync(h->tc_wmax.p, 0, sizeof(float) * (K + 1), h->stream));
+  CU(cudaMemsetAsync(redo_cnt, 0, sizeof(int), h->stream));
+  {
+    ProfScope ps(h, CDAE_K_TOPN_PACK);
+    tc::absmax_cols_kernel<<<std::min<int>(cdiv(h->I, 128), h->sm_count * 4), 256, 0, h->stream>>>(
+        Wd, h->m.bp, h->I, K, h->ld, h->tc_wmax.p);
+    KERNEL_OK(h);
+    tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(
+        Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, reinterpret_cast<__nv_bfloat16*>(h->tc_wb.p));
+    KERNEL_OK(h);
+    tc::pack_z_bf16_kernel<<<cdiv(n_pad * 32, 256), 256, 0, h->stream>>>(
+        h->topn_z.p, users, (int)n_users, n_pad, K, h->ld, Kp, h->tc_wmax.p,
+        reinterpret_cast<__nv_bfloat16*>(h->tc_zb.p), h->tc_eps.p);
+    KERNEL_OK(h);
+  }
+  alignas(64) CUtensorMap ma, mb;
+  TRY(tc_make_map(&ma, h->tc_zb.p, (uint64_t)n_pad, (uint64_t)Kp, tc::TILE_U));
+  TRY(tc_make_map(&mb, h->tc_wb.p, (uint64_t)I_pad, (uint64_t)Kp, tc::TILE_I));
+  tc::TcArgs a;
+  a.n_users = (int)n_users; a.I = h->I; a.n_tiles = (int)(I_pad / tc::TILE_I);
+  a.users = users; a.row_ptr = h->row_ptr_d.p; a.col = h->col_d.p;
+  a.cand_id = h->cand_id.p; a.cand_s = h->cand_s.p; a.cand_cnt = h->cand_cnt.p; a.cand_thr = h->tc_thr.p;
+  const int grid = (int)(n_pad / tc::TILE_U);
+  {
+    ProfScope ps(h, CDAE_K_TOPN);
+    switch (KB) {
+      case 1: TRY(tc_launch<1>(h, ma, mb, a, grid)); break;
+      case 2: TRY(tc_launch<2>(h, ma, mb, a, grid)); break;
+      case 3: TRY(tc_launch<3>(h, ma, mb, a, grid)); break;
+      case 4: TRY(tc_launch<4>(h, ma, mb, a, grid)); break;
+      default: TRY(tc_launch<5>(h, ma, mb, a, grid)); break;
+    }
+    KERNEL_OK(h);
+  }
+  {
+    ProfScope ps(h, CDAE_K_TOPN_RERANK);
+    topn_rerank_kernel<<<cdiv(n_users, 8), 256, 0, h->stream>>>(
+        h->topn_z.p, Wd, h->m.bp, h->K, h->ld, users, (int)n_users, h->cand_id.p, h->cand_cnt.p, tc::CAND_MAX,
+        topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, h->tc_thr.p, h->tc_eps.p, h->tc_redo.p, redo_cnt);
+    KERNEL_OK(h);
+  }
+  CU(cudaMemcpyAsync(n_redo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 extern "C" {
 
 int cdae_topn_build(cdae_handle* h, int32_t topk) {
@@ -34,8 +137,9 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
     n_users = 0;
     for (const MiniBatch& p : h->plan) n_users += p.n_users;
   }
-  TRY(ensure(h, h->cand_id, (size_t)(n_users * TOPN_M)));
-  TRY(ensure(h, h->cand_s, (size_t)(n_users * TOPN_M)));
+  const int64_t slots = std::max<int>(TOPN_M, tc::CAND_MAX);
+  TRY(ensure(h, h->cand_id, (size_t)(n_users * slots)));
+  TRY(ensure(h, h->cand_s, (size_t)(n_users * slots)));
   TRY(ensure(h, h->cand_cnt, (size_t)n_users));
   TRY(ensure(h, h->flag_d, 4));
   TRY(ensure(h, h->topn_ids, (size_t)(h->U * topk)));
@@ -44,11 +148,27 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
   CU(cudaMemsetAsync(h->topn_scores.p, 0, sizeof(float) * h->U * topk, h->stream));
   CU(cudaMemsetAsync(h->flag_d.p, 0, sizeof(int) * 4, h->stream));
   const float* Wd = h->m.asym ? h->m.V : h->m.W;
-  TRY(topn_candidates(h, Wd, users, n_users));
-  topn_rerank_kernel<<<cdiv(n_users, 8), 256, 0, h->stream>>>(
-      h->topn_z.p, Wd, h->m.bp, h->K, h->ld, users, (int)n_users, h->cand_id.p, h->cand_cnt.p, topk,
-      h->topn_ids.p, h->topn_scores.p, h->flag_d.p);
-  KERNEL_OK(h);
+  h->topn_tc_users = h->topn_redo_users = 0;
+  h->topn_path = 0;
+  const int32_t* exact_users = users;
+  int64_t n_exact = n_users;
+  if (n_users > 0 && tc_path_wanted(h, topk)) {
+    int n_redo = 0;
+    TRY(topn_candidates_tc(h, Wd, users, n_users, topk, &n_redo));
+    h->topn_path = 1;
+    h->topn_tc_users = n_users - n_redo;
+    h->topn_redo_users = n_redo;
+    exact_users = h->tc_redo.p;
+    n_exact = n_redo;
+  }
+  if (n_exact > 0) {
+    TRY(topn_candidates(h, Wd, exact_users, n_exact));
+    ProfScope ps(h, CDAE_K_TOPN_RERANK);
+    topn_rerank_kernel<<<cdiv(n_exact, 8), 256, 0, h->stream>>>(
+        h->topn_z.p, Wd, h->m.bp, h->K, h->ld, exact_users, (int)n_exact, h->cand_id.p, h->cand_cnt.p, TOPN_M,
+        topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, nullptr, nullptr, nullptr, nullptr);
+    KERNEL_OK(h);
+  }
   h->topn_ids_h.resize((size_t)(h->U * topk));
   h->topn_scores_h.resize((size_t)(h->U * topk));
   int flag[4] = {0, 0, 0, 0};
@@ -61,6 +181,16 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
   if (flag[0])
     return set_error(CDAE_E_INVALID, "a user has fewer than topk unrated items "
                      "(the reference CHECK-aborts here, cdae.hpp:187)");
+  return 0;
+}
+
+/* Which candidate path the last cdae_topn_build used (1 = tcgen05, 0 = fp32 CUDA cores) and how
+ * many users its error bound verified / how many were redone by the exact kernel. */
+int cdae_topn_stats(cdae_handle* h, int32_t* path, int64_t* verified_users, int64_t* redone_users) {
+  if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  if (path) *path = h->topn_path;
+  if (verified_users) *verified_users = h->topn_tc_users;
+  if (redone_users) *redone_users = h->topn_redo_users;
   return 0;
 }
 

@@ -142,15 +142,25 @@ __global__ void __launch_bounds__(256) topn_tile_fp32_kernel(
 }
 
 // Exact re-rank: fp64 score of each candidate, final top-k by (score desc, id asc).
-// One warp per user.  Returns -1 ids when fewer than topk unrated items exist (the reference
-// CHECK-aborts there, cdae.hpp:187; the host turns it into an error).
+// One warp per user; `stride` = candidate slots per user in cand_id (<= RERANK_MAX).
+// Returns -1 ids when fewer than topk unrated items exist (the reference CHECK-aborts there,
+// cdae.hpp:187; the host turns it into an error).
+//
+// VERIFY mode (thr != nullptr, candidates from the bf16 tensor-core kernel): every unrated item
+// that is not a candidate has APPROXIMATE score <= thr[u] and |approx - exact| <= eps[u], so the
+// list is provably the exact one iff  thr[u] + eps[u] < (k-th best exact candidate score).
+// Users that fail (or have fewer than topk candidates) are appended to redo_list and left
+// untouched; the exact fp32 kernel then handles them.
+constexpr int RERANK_MAX = 96;
 __global__ void __launch_bounds__(256) topn_rerank_kernel(
     const float* __restrict__ Z, const float* __restrict__ Wd, const float* __restrict__ bp, int K,
     int ld, const int32_t* __restrict__ users, int n_users, const int* __restrict__ cand_id,
-    const int* __restrict__ cand_cnt, int topk, int32_t* __restrict__ out_id,
-    float* __restrict__ out_s, int* __restrict__ short_flag) {
-  __shared__ double sc[8][TOPN_M];
-  __shared__ int ids[8][TOPN_M];
+    const int* __restrict__ cand_cnt, int stride, int topk, int32_t* __restrict__ out_id,
+    float* __restrict__ out_s, int* __restrict__ short_flag, const float* __restrict__ thr,
+    const float* __restrict__ eps, int32_t* __restrict__ redo_list, int* __restrict__ redo_cnt) {
+  __shared__ double sc[8][RERANK_MAX];
+  __shared__ int ids[8][RERANK_MAX];
+  __shared__ double kth[8];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * 8 + w;
   if (u >= n_users) return;
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
   const int cnt = cand_cnt[u];
   const float* z = Z + uid * ld;
   for (int c = lane; c < cnt; c += 32) {
-    const int it = cand_id[(int64_t)u * TOPN_M + c];
+    const int it = cand_id[(int64_t)u * stride + c];
     const float* wr = Wd + (int64_t)it * ld;
     double s = 0.;
     for (int k = 0; k < K; ++k) s += (double)wr[k] * (double)z[k];
@@ -167,6 +177,10 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
   }
   __syncwarp();
   if (cnt < topk) {
+    if (thr) {
+      if (lane == 0) redo_list[atomicAdd(redo_cnt, 1)] = (int32_t)uid;
+      return;
+    }
     if (lane == 0) *short_flag = 1;
     for (int t = lane; t < topk; t += 32) {
       out_id[uid * topk + t] = -1;
@@ -174,17 +188,37 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
     }
     return;
   }
-  for (int c = lane; c < cnt; c += 32) {
-    const double s = sc[w][c];
-    const int id = ids[w][c];
-    int rank = 0;
-    for (int o = 0; o < cnt; ++o) {
-      const double so = sc[w][o];
-      rank += (so > s) || (so == s && ids[w][o] < id);
+  int my_rank[(RERANK_MAX + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (RERANK_MAX + 31) / 32; ++i) {
+    const int c = lane + i * 32;
+    my_rank[i] = 1 << 30;
+    if (c < cnt) {
+      const double s = sc[w][c];
+      const int id = ids[w][c];
+      int rank = 0;
+      for (int o = 0; o < cnt; ++o) {
+        const double so = sc[w][o];
+        rank += (so > s) || (so == s && ids[w][o] < id);
+      }
+      my_rank[i] = rank;
+      if (rank == topk - 1) kth[w] = s;
     }
-    if (rank < topk) {
-      out_id[uid * topk + rank] = id;
-      out_s[uid * topk + rank] = (float)s;
+  }
+  __syncwarp();
+  if (thr) {
+    const bool ok = (double)thr[u] + (double)eps[u] < kth[w];
+    if (!ok) {
+      if (lane == 0) redo_list[atomicAdd(redo_cnt, 1)] = (int32_t)uid;
+      return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < (RERANK_MAX + 31) / 32; ++i) {
+    const int c = lane + i * 32;
+    if (c < cnt && my_rank[i] < topk) {
+      out_id[uid * topk + my_rank[i]] = ids[w][c];
+      out_s[uid * topk + my_rank[i]] = (float)sc[w][c];
     }
   }
 }

@@ -1,0 +1,529 @@
+// cdae_b200/csrc/topn_tc.cuh — full-item decode of CDAE::recommend (cdae.hpp:176-186) on the
+// 5th-generation tensor cores: S = Z · W'ᵀ (+ b') for a tile of 128 users against ALL items, with
+// the top-candidate selection fused into the epilogue so the U x I score matrix never exists.
+//
+//   operands  bf16, K-major, 128-byte-swizzled in shared memory (TMA, cp.async.bulk.tensor)
+//             A = Zb  [users_pad][Kp]   Kp = round_up(K + 2, 64); columns K, K+1 hold 1.0
+//             B = Wb  [items_pad][Kp]   columns K, K+1 hold bf16 hi / lo of b'  (bias rides in
+//                                       the contraction, no epilogue add)
+//   MMA       tcgen05.mma.cta_group::1.kind::f16, M = 128 (users) x N = 256 (items) x K = 16,
+//             fp32 accumulators in TMEM, two 256-column buffers (all 512 columns)
+//   roles     warp 0 TMA producer · warp 1 MMA issuer · warps 2-3 rated-item bitmaps (warp 2 also
+//             owns the TMEM allocation) · warps 4-7 epilogue (tcgen05.ld, one TMEM lane = one user
+//             per thread)
+//
+// The scores are APPROXIMATE (bf16 operands).  Exactness of the final lists is restored
+// afterwards (topn_api.inl): the epilogue keeps, per user, every unrated item whose approximate
+// score exceeds a running threshold `thr` (raised by periodic compaction, never lowered), so at
+// the end every unrated item that is NOT a candidate has approx score <= thr; the re-rank kernel
+// scores the candidates in fp64 and accepts the user's list only if  thr + eps_u < (k-th best
+// exact score), eps_u being a rigorous bound on |approx - exact| (pack_z_bf16_kernel).  Users
+// that fail the test are re-done by the exact fp32 kernel.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace cdae {
+namespace tc {
+
+constexpr int TILE_U = 128;   // users per CTA  (UMMA M)
+constexpr int TILE_I = 256;   // items per accumulator tile (UMMA N)
+constexpr int KBLK = 64;      // bf16 elements per 128-byte swizzle row
+constexpr int NSTAGE = 3;     // B k-blocks in flight
+constexpr int A_BLK_BYTES = TILE_U * KBLK * 2;   // 16 KB
+constexpr int B_BLK_BYTES = TILE_I * KBLK * 2;   // 32 KB
+constexpr int MAX_KB = 5;     // Kp <= 320  (K <= 318)
+constexpr int CAND_MAX = 96;  // largest per-user candidate buffer
+
+// per-user candidate slots by number of k-blocks (what is left of the 227 KB after A and B)
+__host__ __device__ constexpr int cand_slots(int kb) {
+  return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? 48 : 40;
+}
+__host__ __device__ constexpr int keep_lo(int kb) { return kb <= 3 ? 24 : 20; }
+__host__ __device__ constexpr int keep_hi(int kb) {
+  return cand_slots(kb) / 2 > keep_lo(kb) + 8 ? cand_slots(kb) / 2 : keep_lo(kb) + 8;
+}
+constexpr int BM_BYTES = 2 * 8 * TILE_U * 4;  // two rated bitmaps [8 words][128 rows]
+__host__ __device__ constexpr size_t smem_bytes(int kb) {
+  return 1024 /*alignment slack*/ + (size_t)kb * A_BLK_BYTES + (size_t)NSTAGE * B_BLK_BYTES +
+         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + 256 /*barriers*/;
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+// start address >> 4 in [0,14); LBO (unused for swizzled K-major) in [16,30); SBO = 1024 B (eight
+// 128-byte rows) >> 4 in [32,46); descriptor version 1 in [46,48); layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A and B bf16
+// (bits 7-9 = 1, 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+// Operand packing.
+// Column-wise max |W'| (K values) and max |b'|, for the error bound.  out[K] = bmax.
+__global__ void __launch_bounds__(256) absmax_cols_kernel(const float* __restrict__ W, const float* __restrict__ bp,
+                                                          int64_t I, int K, int ld, float* __restrict__ out) {
+  // block handles a slab of rows; thread t handles columns t, t+256, ...
+  const int64_t rows_per_block = (I + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(I, r0 + rows_per_block);
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+    float m = 0.f;
+    if (k < K) {
+      for (int64_t r = r0; r < r1; ++r) m = fmaxf(m, fabsf(W[r * ld + k]));
+    } else {
+      for (int64_t r = r0; r < r1; ++r) m = fmaxf(m, fabsf(bp[r]));
+    }
+    atomicMax(reinterpret_cast<int*>(out + k), __float_as_int(m));  // non-negative floats order as ints
+  }
+}
+
+// Wb[i][0..K) = bf16(W'[i]), Wb[i][K] = bf16(b'[i]), Wb[i][K+1] = bf16(b'[i] - hi); rows >= I and
+// the remaining pad columns are 0.  One thread per (row, 8-column group).
+__global__ void __launch_bounds__(256) pack_w_bf16_kernel(const float* __restrict__ W, const float* __restrict__ bp,
+                                                          int64_t I, int64_t I_pad, int K, int ld, int Kp,
+                                                          __nv_bfloat16* __restrict__ out) {
+  const int g8 = Kp / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I_pad * g8) return;
+  const int64_t r = idx / g8;
+  const int c0 = (int)(idx % g8) * 8;
+  __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float v = 0.f;
+    if (r < I) {
+      if (c < K) v = W[r * ld + c];
+      else if (c == K) v = bp[r];
+      else if (c == K + 1) {
+        const float b = bp[r];
+        v = b - __bfloat162float(__float2bfloat16_rn(b));
+      }
+    }
+    o[j] = __float2bfloat16_rn(v);
+  }
+  *reinterpret_cast<uint4*>(out + r * Kp + c0) = *reinterpret_cast<const uint4*>(o);
+}
+
+// Zb[r][0..K) = bf16(z of user r), Zb[r][K] = Zb[r][K+1] = 1; rows >= n are 0.  Also the per-user
+// error bound: approx = sum_k bf16(z_k) bf16(w_k) + bhi + blo accumulated in fp32 by the tensor core;
+//   |approx - exact| <= (2^-8 * 1.01 + (Kp + 2) * 2^-22) * sum_k |z_k| wmax_k   (operand rounding 2^-9
+//   each, product exact, fp32 accumulation)  +  (2^-16 + (Kp + 2) * 2^-22) * bmax   (bias residual).
+// One warp per user.
+__global__ void __launch_bounds__(256) pack_z_bf16_kernel(const float* __restrict__ Z, const int32_t* __restrict__ users,
+                                                          int n, int64_t n_pad, int K, int ld, int Kp,
+                                                          const float* __restrict__ wmax /*[K+1]*/,
+                                                          __nv_bfloat16* __restrict__ out, float* __restrict__ eps) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_pad) return;
+  float acc = 0.f;
+  const float* z = nullptr;
+  if (r < n) z = Z + (int64_t)(users ? users[r] : r) * ld;
+  for (int c = lane; c < Kp; c += 32) {
+    float v = 0.f;
+    if (z) {
+      if (c < K) {
+        v = z[c];
+        acc += fabsf(v) * wmax[c];
+      } else if (c <= K + 1) {
+        v = 1.f;
+      }
+    }
+    out[r * Kp + c] = __float2bfloat16_rn(v);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0 && r < n) {
+    const float slack = (float)(Kp + 2) * 2.3841858e-7f;  // 2^-22
+    eps[r] = (0.00390625f * 1.01f + slack) * acc + (1.52587890625e-5f + slack) * wmax[K];
+  }
+}
+
+// Compaction of the per-user candidate buffers, called by a whole epilogue warp with every lane
+// working on its own row: raise thr to a value t with KEEP_LO <= #{s > t} <= KEEP_HI (bisection on
+// the value) and drop the entries <= t.  thr never decreases, so "every non-candidate has
+// approx <= thr" is preserved.  If the bisection cannot separate (many equal scores) the cut goes
+// ABOVE the tie group: fewer than KEEP_LO entries survive and the verification step later sends
+// that user to the exact path.
+template <int C, int KEEP_LO, int KEEP_HI>
+__device__ __noinline__ void compact(float* bs, int* bi, int* cnt_io, float* thr_io) {
+  int cnt = *cnt_io;
+  float thr = *thr_io;
+  float mn = INFINITY, hi = -INFINITY;
+  for (int e = 0; e < C; ++e)
+    if (e < cnt) {
+      const float s = bs[e * TILE_U];
+      mn = fminf(mn, s);
+      hi = fmaxf(hi, s);
+    }
+  const bool need = cnt > KEEP_HI;
+  bool done = !need;
+  // count(s > lo) > KEEP_HI  and  count(s > hi) = 0 < KEEP_LO
+  float lo = (thr == -INFINITY) ? mn - 1.f : thr;
+  float tnew = thr;
+  for (int it = 0; it < 26; ++it) {
+    if (__all_sync(0xffffffffu, done)) break;
+    const float mid = 0.5f * (lo + hi);
+    int k = 0;
+    for (int e = 0; e < C; ++e)
+      if (e < cnt) k += bs[e * TILE_U] > mid;
+    if (!done) {
+      if (k > KEEP_HI) lo = mid;
+      else if (k < KEEP_LO) hi = mid;
+      else { tnew = mid; done = true; }
+    }
+  }
+  if (need && !done) tnew = hi;
+  if (tnew > thr) {
+    int w = 0;
+    for (int e = 0; e < C; ++e)
+      if (e < cnt) {
+        const float s = bs[e * TILE_U];
+        const int id = bi[e * TILE_U];
+        if (s > tnew) {
+          bs[w * TILE_U] = s;
+          bi[w * TILE_U] = id;
+          ++w;
+        }
+      }
+    cnt = w;
+    thr = tnew;
+  }
+  *cnt_io = cnt;
+  *thr_io = thr;
+}
+
+// ---------------------------------------------------------------------------------------
+struct TcArgs {
+  int n_users;                 // valid rows of Zb
+  int64_t I;                   // valid items
+  int n_tiles;                 // ceil(I / 256)
+  const int32_t* users;        // nullable: row r of Zb is user users[r]
+  const int64_t* row_ptr;      // train CSR (rated items)
+  const int32_t* col;
+  int* cand_id;                // [n_users][CAND_MAX]
+  float* cand_s;               // [n_users][CAND_MAX]  approximate scores
+  int* cand_cnt;               // [n_users]
+  float* cand_thr;             // [n_users]  final threshold (every non-candidate has approx <= thr)
+};
+
+template <int KB>
+__global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                         const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+  constexpr int C = cand_slots(KB), KEEP_LO = keep_lo(KB), KEEP_HI = keep_hi(KB);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                   // KB x [128][64] bf16, swizzled
+  unsigned char* sB = sA + KB * A_BLK_BYTES;                  // NSTAGE x [256][64] bf16
+  float* cs = reinterpret_cast<float*>(sB + NSTAGE * B_BLK_BYTES);  // [C][128]
+  int* ci = reinterpret_cast<int*>(cs + C * TILE_U);               // [C][128]
+  uint32_t* bm = reinterpret_cast<uint32_t*>(ci + C * TILE_U);     // [2][8][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bm + 2 * 8 * TILE_U);
+  uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
+  uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA -> TMA
+  uint64_t* a_full = bars + 2 * NSTAGE;  // A tile landed
+  uint64_t* t_full = a_full + 1;         // [2] accumulator ready      MMA -> epilogue
+  uint64_t* t_empty = t_full + 2;        // [2] accumulator drained    epilogue -> MMA
+  uint64_t* b_full = t_empty + 2;        // [2] bitmap ready           helpers -> epilogue
+  uint64_t* b_empty = b_full + 2;        // [2] bitmap consumed        epilogue -> helpers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TILE_U;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(a_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full + b, 1);
+      mbar_init(t_empty + b, 4);   // one arrive per epilogue warp
+      mbar_init(b_full + b, 64);   // every helper thread
+      mbar_init(b_empty + b, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_full, KB * A_BLK_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_BLK_BYTES, &map_a, a_full, kb * KBLK, u0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < a.n_tiles; ++t) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_arrive_expect_tx(full + s, B_BLK_BYTES);
+          tma_load_2d(sB + s * B_BLK_BYTES, &map_b, full + s, kb * KBLK, t * TILE_I);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_U, TILE_I);
+      mbar_wait(a_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < a.n_tiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(t_empty + buf, ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)buf * TILE_I;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + kb * A_BLK_BYTES), b0 = smem_u32(sB + s * B_BLK_BYTES);
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k)  // 16 bf16 = 32 bytes along K inside the swizzle row
+            umma_bf16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+          umma_commit(empty + s);  // frees the B stage once these MMAs have read it
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+        umma_commit(t_full + buf);
+      }
+    }
+  } else if (warp < 4) {
+    // ===== rated-item bitmaps: thread h owns rows h and h + 64 =====
+    const int h = threadIdx.x - 64;
+    int pos[2], end[2], nxt[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int r = h + q * 64;
+      pos[q] = end[q] = 0;
+      nxt[q] = 0x7fffffff;
+      if (u0 + r < a.n_users) {
+        const int64_t uid = a.users ? a.users[u0 + r] : (u0 + r);
+        const int64_t p0 = a.row_ptr[uid], p1 = a.row_ptr[uid + 1];
+        pos[q] = 0;
+        end[q] = (int)(p1 - p0);
+        // keep pos relative to the row start; col pointer recomputed below
+        if (end[q] > 0) nxt[q] = a.col[p0];
+      }
+    }
+    for (int t = 0; t < a.n_tiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(b_empty + buf, ((t >> 1) & 1) ^ 1);
+      const int64_t i0 = (int64_t)t * TILE_I;
+      uint32_t* my = bm + buf * 8 * TILE_U;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int r = h + q * 64;
+        uint32_t w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          // columns that are not items at all (the padded tail of the last tile)
+          const int64_t first = i0 + c * 32;
+          w[c] = first + 32 <= a.I ? 0u : (first >= a.I ? 0xffffffffu : (0xffffffffu << (int)(a.I - first)));
+        }
+        if (nxt[q] < i0 + TILE_I) {
+          const int64_t uid = a.users ? a.users[u0 + r] : (u0 + r);
+          const int32_t* row = a.col + a.row_ptr[uid];
+          while (nxt[q] < i0 + TILE_I) {
+            const int rel = (int)(nxt[q] - i0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if ((rel >> 5) == c) w[c] |= 1u << (rel & 31);
+            ++pos[q];
+            nxt[q] = pos[q] < end[q] ? row[pos[q]] : 0x7fffffff;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) my[c * TILE_U + r] = w[c];
+      }
+      mbar_arrive(b_full + buf);
+    }
+  } else {
+    // ===== epilogue: thread = one user (TMEM lane), keeps the user's candidate buffer =====
+    const int q = warp - 4;                 // TMEM lane quadrant of this warp (= warp % 4)
+    const int row = q * 32 + lane;
+    float* bs = cs + row;                   // entry e at bs[e * 128]
+    int* bi = ci + row;
+    float thr = -INFINITY;
+    int cnt = 0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    for (int t = 0; t < a.n_tiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t par = (t >> 1) & 1;
+      mbar_wait(t_full + buf, par);
+      mbar_wait(b_full + buf, par);
+      tc_fence_after();
+      const uint32_t* my_bm = bm + buf * 8 * TILE_U + row;
+      const int item0 = t * TILE_I;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)(buf * TILE_I + c * 32), v);
+        float gm[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float x0 = max3(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
+          const float x1 = max3(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          gm[g] = max3(x0, x1, fmaxf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        }
+        const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+        if (__any_sync(0xffffffffu, m > thr)) {
+          const uint32_t rated = my_bm[c * TILE_U];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
+            // invariant here: cnt <= C - 8
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float s = __uint_as_float(v[g * 8 + j]);
+              if (s > thr && !((rated >> (g * 8 + j)) & 1u)) {
+                bs[cnt * TILE_U] = s;
+                bi[cnt * TILE_U] = item0 + c * 32 + g * 8 + j;
+                ++cnt;
+              }
+            }
+            if (__any_sync(0xffffffffu, cnt > C - 8)) compact<C, KEEP_LO, KEEP_HI>(bs, bi, &cnt, &thr);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(t_empty + buf);
+        mbar_arrive(b_empty + buf);
+      }
+    }
+    // ---- write the candidates out
+    if (u0 + row < a.n_users) {
+      const int64_t o = (int64_t)(u0 + row) * CAND_MAX;
+      for (int e = 0; e < cnt; ++e) {
+        a.cand_id[o + e] = bi[e * TILE_U];
+        a.cand_s[o + e] = bs[e * TILE_U];
+      }
+      a.cand_cnt[u0 + row] = cnt;
+      a.cand_thr[u0 + row] = thr;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace cdae

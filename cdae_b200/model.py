@@ -235,6 +235,13 @@ class CDAE:
         _lib.check(self._L.cdae_topn_fetch(self._h, _ptr(ids, _lib.i64p), _ptr(sc, _lib.f32p)))
         return ids, sc
 
+    def topn_stats(self):
+        """(path, verified_users, redone_users) of the last pre_recommend: path 1 = tcgen05
+        candidates proven exact by the error bound, 0 = fp32 CUDA-core kernel."""
+        p, a, b = C.c_int32(), C.c_int64(), C.c_int64()
+        _lib.check(self._L.cdae_topn_stats(self._h, C.byref(p), C.byref(a), C.byref(b)))
+        return p.value, a.value, b.value
+
     def topn_evaluate(self, test_row_ptr, test_col):
         """TOPN_Evaluation::evaluate on the stored lists: [P@1,P@5,P@10,R@1,R@5,R@10,MAP@5,MAP@10]."""
         rp = _arr(test_row_ptr, np.int64)

@@ -164,6 +164,11 @@ int cdae_penalty_loss(cdae_handle* h, double* out);
  * score descending.  cdae_topn_lookup copies one user's list (thread-safe). */
 int cdae_topn_build(cdae_handle* h, int32_t topk);
 int cdae_topn_lookup(cdae_handle* h, int64_t uid, int64_t* ids_out, float* scores_out);
+/* The candidate phase of the last cdae_topn_build: path 1 = bf16 tcgen05/TMEM contraction whose
+ * lists are PROVEN exact per user by an error bound (verified_users), the rest (redone_users)
+ * recomputed by the exact fp32 kernel; path 0 = fp32 kernel for everyone (K > 318, topk > 16, or
+ * CDAE_B200_TOPN=fp32 in the environment). */
+int cdae_topn_stats(cdae_handle* h, int32_t* path, int64_t* verified_users, int64_t* redone_users);
 /* Whole table, U x topk (ids) and U x topk (scores; nullable). */
 int cdae_topn_fetch(cdae_handle* h, int64_t* ids_out, float* scores_out);
 /* TOPN_Evaluation::evaluate (evaluation.hpp:113-181) on the built table against a test CSR:
@@ -184,7 +189,8 @@ int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl
  * the summed milliseconds and the number of launches since cdae_profile(h, 1). */
 enum cdae_kernel_class {
   CDAE_K_SAMPLE = 0, CDAE_K_GATHER, CDAE_K_ACTIVATE, CDAE_K_DECODE, CDAE_K_HIDDEN_BWD,
-  CDAE_K_SCATTER, CDAE_K_ALLREDUCE, CDAE_K_APPLY, CDAE_K_TOPN, CDAE_K_COUNT
+  CDAE_K_SCATTER, CDAE_K_ALLREDUCE, CDAE_K_APPLY, CDAE_K_TOPN /* candidate kernel */,
+  CDAE_K_TOPN_PACK, CDAE_K_TOPN_RERANK, CDAE_K_COUNT
 };
 int cdae_profile(cdae_handle* h, int32_t enable);
 int cdae_profile_get(cdae_handle* h, double* ms_out /*[CDAE_K_COUNT]*/,
