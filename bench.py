@@ -45,11 +45,29 @@ def workload_name(n_gpus):
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, source) — driver-measured, else the profiling recipe's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def decode_kernel_name(K):
+    """The <G,NV> instantiation DISPATCH_LD (csrc/api.cu) picks for this K."""
+    lines = ((K + 31) // 32 * 32) // 32
+    g, nv = ((8, lines) if lines <= 4 else (16, 3) if lines <= 6 else (16, 4) if lines <= 8
+             else (32, 3) if lines <= 12 else (32, 4))
+    return "decode_kernel<%d,%d,TRAIN,SAMPLED>" % (g, nv)
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel)
+    return (d["dram_bytes_per_launch"], d["source"]) if d else (None, None)
 
 
 class ClockSampler:
@@ -250,7 +268,7 @@ def run_ours(args):
     if rank == 0:
         value = users_all / (dev_ms / 1e3)
         e2e = users_all / (e2e_ms / 1e3)
-        peak, peak_src = measured_peaks()
+        peak, peak_tf, peak_src = measured_peaks()
         # dominant kernel: sampled decode.  Algorithmic bytes:
         # outputs * (P*4K + P*4 + 4), P = 4 row passes with AdaGrad.
         dec_ms, dec_n = prof["decode"]
@@ -258,9 +276,13 @@ def run_ours(args):
         out_rank0 = outputs_all / world
         alg_bytes = out_rank0 * (P * 4 * K + P * 4 + 4)
         achieved = alg_bytes / (dec_ms / 1e3) / 1e9 if dec_ms > 0 else None
-        roofline = {"bound": "hbm", "kernel": "decode_kernel<16,1,true>", "achieved": achieved,
+        traffic, traffic_src = ncu_traffic("decode_kernel")
+        roofline = {"bound": "hbm", "kernel": decode_kernel_name(K), "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak if achieved else None, "traffic": None,
+                    "frac": achieved / peak if achieved else None, "traffic": traffic,
+                    "traffic_source": traffic_src,
+                    "note": "item tables + gradients (38 MB) are L2-resident: DRAM traffic is far below the "
+                            "algorithmic bytes, so frac on algorithmic bytes can exceed 1",
                     "launches": dec_n, "avg_launch_ms": dec_ms / dec_n if dec_n else None,
                     "algorithmic_bytes_per_launch": alg_bytes / dec_n if dec_n else None,
                     "kernel_ms_share": {k: v[0] / dev_ms for k, v in prof.items() if v[1]}}
@@ -277,6 +299,8 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_topn:
+            line["topn"] = topn_section(m, U, peak_tf, peak_src)
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
             orc.build(ref=False)
@@ -290,6 +314,33 @@ def run_ours(args):
     return 0
 
 
+def topn_section(m, U, peak_tf, peak_src):
+    """Secondary measurement (not part of the timed training step): CDAE::recommend for all users,
+    i.e. the full-item decode on tcgen05 (csrc/topn_tc.cuh), against the measured bf16 peak."""
+    m.pre_recommend(10)                                       # warm-up (allocations, tensor maps)
+    m.profile(True)
+    reps = 3
+    for _ in range(reps):
+        m.pre_recommend(10)
+    prof = m.profile_get()
+    m.profile(False)
+    path, verified, redone = m.topn_stats()
+    ms = prof["topn"][0] / reps
+    kp = (K + 2 + 63) // 64 * 64
+    alg = 2.0 * U * ITEMS * K                                  # SURVEY 8d: 2*I*K flops per user
+    out = {"what": "CDAE::recommend, all users x all items, top-10 (cdae_topn_build)",
+           "path": "tcgen05 bf16 + exact fp64 re-rank" if path == 1 else "fp32 CUDA cores",
+           "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank")) / reps / 1e3),
+           "candidate_kernel_ms": ms, "verified_users": verified, "redone_exact_users": redone,
+           "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel<%d>" % (kp // 64),
+                        "achieved": alg / (ms / 1e3) / 1e12 if ms > 0 else None, "peak": peak_tf,
+                        "peak_source": peak_src + ", burst", "unit": "TFLOP/s",
+                        "frac": alg / (ms / 1e3) / 1e12 / peak_tf if ms > 0 else None,
+                        "executed_tflops_padded_k": 2.0 * U * ITEMS * kp / (ms / 1e3) / 1e12 if ms > 0 else None,
+                        "traffic": ncu_traffic("topn_tc_kernel")[0]}}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,6 +351,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=30000,
                     help="users in the bounded CPU-baseline sample (about 10-15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-topn", action="store_true", help="skip the recommend (full-item decode) section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
