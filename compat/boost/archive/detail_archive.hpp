@@ -53,6 +53,13 @@ class oarchive_impl {
     put(t);
     return *this;
   }
+  // split_member() compiles BOTH halves for every archive (runtime branch on is_saving); the
+  // load half of an output archive is never executed.
+  template <class T>
+  oarchive_impl& operator>>(T&) {
+    archive_fail("operator>> on an output archive");
+    return *this;
+  }
 
  private:
   template <class T>
@@ -137,7 +144,12 @@ class iarchive_impl {
   }
   template <class T>
   iarchive_impl& operator&(T& t) {
-    get(t);
+    get(const_cast<typename std::remove_const<T>::type&>(t));  // save half streams const members
+    return *this;
+  }
+  template <class T>
+  iarchive_impl& operator<<(const T&) {
+    archive_fail("operator<< on an input archive");
     return *this;
   }
 

@@ -21,19 +21,12 @@ class access {
     t.load(ar, version);
   }
 };
-// Tag dispatch on Archive::is_saving so only the matching half is instantiated (the save half
-// streams const members, which an input archive cannot bind).
-template <class Archive, class T>
-inline void split_member_impl(Archive& ar, T& t, const unsigned int version, std::true_type) {
-  access::member_save(ar, t, version);
-}
-template <class Archive, class T>
-inline void split_member_impl(Archive& ar, T& t, const unsigned int version, std::false_type) {
-  access::member_load(ar, t, version);
-}
 template <class Archive, class T>
 inline void split_member(Archive& ar, T& t, const unsigned int version) {
-  split_member_impl(ar, t, version, typename Archive::is_saving());
+  if (Archive::is_saving::value)
+    access::member_save(ar, t, version);
+  else
+    access::member_load(ar, t, version);
 }
 template <class T>
 struct array_wrapper {
