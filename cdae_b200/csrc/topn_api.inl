@@ -61,7 +61,7 @@ static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& m
     CU(cudaFuncSetAttribute(tc::topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  tc::topn_tc_kernel<KB><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
+  tc::topn_tc_kernel<KB><<<grid, tc::n_threads(KB), dyn, h->stream>>>(ma, mb, a);
   return 0;
 }
 

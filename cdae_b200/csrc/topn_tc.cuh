@@ -37,18 +37,23 @@ constexpr int B_BLK_BYTES = TILE_I * KBLK * 2;   // 32 KB
 constexpr int MAX_KB = 5;     // Kp <= 320  (K <= 318)
 constexpr int CAND_MAX = 96;  // largest per-user candidate buffer
 
-// per-user candidate slots by number of k-blocks (what is left of the 227 KB after A and B)
+// Epilogue warps per TMEM lane quadrant: two while shared memory leaves room for two candidate
+// buffers per user (each warp of a pair takes every other 32-column chunk and keeps its own
+// buffer and threshold), one for the widest operands.
+__host__ __device__ constexpr int epi_warps(int kb) { return kb <= 3 ? 2 : 1; }
+// candidate slots per user (all buffers together): what is left of the 227 KB after A and B
 __host__ __device__ constexpr int cand_slots(int kb) {
   return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? 48 : 40;
 }
-__host__ __device__ constexpr int keep_lo(int kb) { return kb <= 3 ? 24 : 20; }
-__host__ __device__ constexpr int keep_hi(int kb) {
-  return cand_slots(kb) / 2 > keep_lo(kb) + 8 ? cand_slots(kb) / 2 : keep_lo(kb) + 8;
-}
+__host__ __device__ constexpr int buf_slots(int kb) { return cand_slots(kb) / epi_warps(kb); }
+// a compaction keeps between keep_lo and keep_hi entries of a buffer
+__host__ __device__ constexpr int keep_hi(int kb) { return buf_slots(kb) / 2; }
+__host__ __device__ constexpr int keep_lo(int kb) { return keep_hi(kb) - 8 > 12 ? keep_hi(kb) - 8 : 12; }
+__host__ __device__ constexpr int n_threads(int kb) { return 128 + 128 * epi_warps(kb); }
 constexpr int BM_BYTES = 2 * 8 * TILE_U * 4;  // two rated bitmaps [8 words][128 rows]
 __host__ __device__ constexpr size_t smem_bytes(int kb) {
   return 1024 /*alignment slack*/ + (size_t)kb * A_BLK_BYTES + (size_t)NSTAGE * B_BLK_BYTES +
-         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + 256 /*barriers*/;
+         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + 2 * TILE_U * 8 /*merge*/ + 256 /*barriers*/;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -122,8 +127,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// 32 consecutive fp32 columns of this thread's TMEM lane: issue, then wait.  The wait names the
+// destination registers as in/out operands so the compiler cannot move their uses above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -134,7 +140,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+                 "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),
+                 "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),
+                 "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
@@ -310,18 +328,54 @@ struct TcArgs {
   float* cand_thr;             // [n_users]  final threshold (every non-candidate has approx <= thr)
 };
 
+// One 32-column chunk of one accumulator tile for this thread's user: fast reject by the chunk
+// maximum, else scan the 8-column groups that hold a score above thr.  Warp-uniform control flow
+// (votes), so a compaction can run for the whole warp between groups.
+template <int C2, int KEEP_LO, int KEEP_HI>
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t rated, int item_base, float* bs,
+                                           int* bi, int& cnt, float& thr) {
+  float gm[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float x0 = max3(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
+    const float x1 = max3(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+    gm[g] = max3(x0, x1, fmaxf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+  }
+  const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+  if (!__any_sync(0xffffffffu, m > thr)) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
+    // invariant here: cnt <= C2 - 8
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = __uint_as_float(v[g * 8 + j]);
+      if (s > thr && !((rated >> (g * 8 + j)) & 1u)) {
+        bs[cnt * TILE_U] = s;
+        bi[cnt * TILE_U] = item_base + g * 8 + j;
+        ++cnt;
+      }
+    }
+    if (__any_sync(0xffffffffu, cnt > C2 - 8)) compact<C2, KEEP_LO, KEEP_HI>(bs, bi, &cnt, &thr);
+  }
+}
+
 template <int KB>
-__global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                         const __grid_constant__ CUtensorMap map_b, TcArgs a) {
-  constexpr int C = cand_slots(KB), KEEP_LO = keep_lo(KB), KEEP_HI = keep_hi(KB);
+__global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+  constexpr int C = cand_slots(KB), EPI = epi_warps(KB), C2 = buf_slots(KB);
+  constexpr int KEEP_LO = keep_lo(KB), KEEP_HI = keep_hi(KB);
+  static_assert(KEEP_HI <= C2 - 8 && KEEP_LO >= 10 && KEEP_LO < KEEP_HI, "candidate buffer geometry");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                   // KB x [128][64] bf16, swizzled
   unsigned char* sB = sA + KB * A_BLK_BYTES;                  // NSTAGE x [256][64] bf16
-  float* cs = reinterpret_cast<float*>(sB + NSTAGE * B_BLK_BYTES);  // [C][128]
-  int* ci = reinterpret_cast<int*>(cs + C * TILE_U);               // [C][128]
+  float* cs = reinterpret_cast<float*>(sB + NSTAGE * B_BLK_BYTES);  // [EPI][C2][128]
+  int* ci = reinterpret_cast<int*>(cs + C * TILE_U);               // [EPI][C2][128]
   uint32_t* bm = reinterpret_cast<uint32_t*>(ci + C * TILE_U);     // [2][8][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bm + 2 * 8 * TILE_U);
+  int* mcnt = reinterpret_cast<int*>(bm + 2 * 8 * TILE_U);          // [2][128] final counts per buffer
+  float* mthr = reinterpret_cast<float*>(mcnt + 2 * TILE_U);        // [2][128] final thresholds
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mthr + 2 * TILE_U);
   uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA -> TMA
   uint64_t* a_full = bars + 2 * NSTAGE;  // A tile landed
@@ -346,9 +400,9 @@ __global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__
     mbar_init(a_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(t_full + b, 1);
-      mbar_init(t_empty + b, 4);   // one arrive per epilogue warp
-      mbar_init(b_full + b, 64);   // every helper thread
-      mbar_init(b_empty + b, 4);
+      mbar_init(t_empty + b, 4 * EPI);  // one arrive per epilogue warp
+      mbar_init(b_full + b, 64);        // every helper thread
+      mbar_init(b_empty + b, 4 * EPI);
     }
     fence_barrier_init();
   }
@@ -411,9 +465,7 @@ __global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__
       if (u0 + r < a.n_users) {
         const int64_t uid = a.users ? a.users[u0 + r] : (u0 + r);
         const int64_t p0 = a.row_ptr[uid], p1 = a.row_ptr[uid + 1];
-        pos[q] = 0;
         end[q] = (int)(p1 - p0);
-        // keep pos relative to the row start; col pointer recomputed below
         if (end[q] > 0) nxt[q] = a.col[p0];
       }
     }
@@ -450,14 +502,17 @@ __global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__
       mbar_arrive(b_full + buf);
     }
   } else {
-    // ===== epilogue: thread = one user (TMEM lane), keeps the user's candidate buffer =====
-    const int q = warp - 4;                 // TMEM lane quadrant of this warp (= warp % 4)
+    // ===== epilogue: thread = one user (TMEM lane); warp pair member `hf` takes chunks hf, hf+EPI, ..
+    const int e = warp - 4;
+    const int q = e & 3;                    // TMEM lane quadrant (= warp % 4)
+    const int hf = e >> 2;                  // which buffer / which chunks
     const int row = q * 32 + lane;
-    float* bs = cs + row;                   // entry e at bs[e * 128]
-    int* bi = ci + row;
+    float* bs = cs + hf * C2 * TILE_U + row;   // entry e at bs[e * 128]
+    int* bi = ci + hf * C2 * TILE_U + row;
     float thr = -INFINITY;
     int cnt = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int NCH = 8 / EPI;            // chunks per tile for this warp
 
     for (int t = 0; t < a.n_tiles; ++t) {
       const int buf = t & 1;
@@ -467,36 +522,19 @@ __global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t* my_bm = bm + buf * 8 * TILE_U + row;
       const int item0 = t * TILE_I;
+      const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I);
+      // two chunks in flight: the next tcgen05.ld is issued before the current chunk is scanned
+      uint32_t va[32], vb[32];
+      tmem_ld32_issue(col0 + (uint32_t)(hf * 32), va);
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)(buf * TILE_I + c * 32), v);
-        float gm[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float x0 = max3(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
-          const float x1 = max3(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-          gm[g] = max3(x0, x1, fmaxf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
-        }
-        const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-        if (__any_sync(0xffffffffu, m > thr)) {
-          const uint32_t rated = my_bm[c * TILE_U];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
-            // invariant here: cnt <= C - 8
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float s = __uint_as_float(v[g * 8 + j]);
-              if (s > thr && !((rated >> (g * 8 + j)) & 1u)) {
-                bs[cnt * TILE_U] = s;
-                bi[cnt * TILE_U] = item0 + c * 32 + g * 8 + j;
-                ++cnt;
-              }
-            }
-            if (__any_sync(0xffffffffu, cnt > C - 8)) compact<C, KEEP_LO, KEEP_HI>(bs, bi, &cnt, &thr);
-          }
-        }
+      for (int i = 0; i < NCH; i += 2) {
+        const int c0 = hf + i * EPI, c1 = hf + (i + 1) * EPI;
+        tmem_ld_wait(va);
+        tmem_ld32_issue(col0 + (uint32_t)(c1 * 32), vb);
+        scan_chunk<C2, KEEP_LO, KEEP_HI>(va, my_bm[c0 * TILE_U], item0 + c0 * 32, bs, bi, cnt, thr);
+        tmem_ld_wait(vb);
+        if (i + 2 < NCH) tmem_ld32_issue(col0 + (uint32_t)((c1 + EPI) * 32), va);
+        scan_chunk<C2, KEEP_LO, KEEP_HI>(vb, my_bm[c1 * TILE_U], item0 + c1 * 32, bs, bi, cnt, thr);
       }
       tc_fence_before();
       __syncwarp();
@@ -505,15 +543,28 @@ __global__ void __launch_bounds__(256, 1) topn_tc_kernel(const __grid_constant__
         mbar_arrive(b_empty + buf);
       }
     }
-    // ---- write the candidates out
+    // ---- merge the buffers of the warp pair and write the candidates out
+    mcnt[hf * TILE_U + row] = cnt;
+    mthr[hf * TILE_U + row] = thr;
+    named_bar_sync(1, 128 * EPI);
     if (u0 + row < a.n_users) {
-      const int64_t o = (int64_t)(u0 + row) * CAND_MAX;
-      for (int e = 0; e < cnt; ++e) {
-        a.cand_id[o + e] = bi[e * TILE_U];
-        a.cand_s[o + e] = bs[e * TILE_U];
+      int off = 0, total = 0;
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int x = 0; x < EPI; ++x) {
+        if (x < hf) off += mcnt[x * TILE_U + row];
+        total += mcnt[x * TILE_U + row];
+        tmax = fmaxf(tmax, mthr[x * TILE_U + row]);
       }
-      a.cand_cnt[u0 + row] = cnt;
-      a.cand_thr[u0 + row] = thr;
+      const int64_t o = (int64_t)(u0 + row) * CAND_MAX + off;
+      for (int x = 0; x < cnt; ++x) {
+        a.cand_id[o + x] = bi[x * TILE_U];
+        a.cand_s[o + x] = bs[x * TILE_U];
+      }
+      if (hf == 0) {
+        a.cand_cnt[u0 + row] = total;
+        a.cand_thr[u0 + row] = tmax;   // every non-candidate of either half has approx <= its half's thr
+      }
     }
   }
 
