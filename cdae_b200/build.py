@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + SOURCES + ["-o", SO, "-ldl"]
+    extra = os.environ.get("CDAE_NVCC_FLAGS", "").split()     # e.g. -DDECODE_MIN_BLOCKS=2 for A/B runs
+    cmd = [nvcc] + NVCC_FLAGS + extra + SOURCES + ["-o", SO, "-ldl"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

@@ -281,6 +281,14 @@ static BatchDev make_batch(cdae_handle* h, const WorkItem* in, int64_t n_in, con
   return bt;
 }
 
+// Leading dimension for K columns: whole 128-byte lines, rounded up to a size one <G,NV>
+// geometry covers exactly (4*G*NV floats), so the kernels need no column bound checks.
+static int row_stride(int K) {
+  const int lines = (K + 31) / 32;
+  const int l = lines <= 4 ? lines : lines <= 6 ? 6 : lines <= 8 ? 8 : lines <= 12 ? 12 : 16;
+  return l * 32;
+}
+
 // launch one of the <G,NV> row-geometry instantiations by leading dimension (ld is a multiple
 // of 32 floats): a warp-level 16-byte access covers one 128-byte line per row with G = 8 lanes,
 // two lines with 16, four with 32; NV = vectors per lane.
@@ -331,15 +339,26 @@ static int launch_decode(cdae_handle* h, const BatchDev& bt, bool train, const S
   const int grid = cdiv((int64_t)bt.n_out_items * 32, 256);
   SampleArgs none{};
   if (train && sa) {
-#define CALL(G, NV) decode_kernel<G, NV, true, true><<<grid, 256, 0, h->stream>>>(h->m, bt, *sa, h->stats_d)
-    DISPATCH_LD(h->ld, CALL);
+    // the epoch path: loss fixed at compile time for the two losses CDAE is used with
+    if (h->m.loss == LOSS_CE) {
+#define CALL(G, NV) decode_kernel<G, NV, true, true, LOSS_CE><<<grid, 256, 0, h->stream>>>(h->m, bt, *sa, h->stats_d)
+      DISPATCH_LD(h->ld, CALL);
 #undef CALL
+    } else if (h->m.loss == LOSS_SQUARE) {
+#define CALL(G, NV) decode_kernel<G, NV, true, true, LOSS_SQUARE><<<grid, 256, 0, h->stream>>>(h->m, bt, *sa, h->stats_d)
+      DISPATCH_LD(h->ld, CALL);
+#undef CALL
+    } else {
+#define CALL(G, NV) decode_kernel<G, NV, true, true, -1><<<grid, 256, 0, h->stream>>>(h->m, bt, *sa, h->stats_d)
+      DISPATCH_LD(h->ld, CALL);
+#undef CALL
+    }
   } else if (train) {
-#define CALL(G, NV) decode_kernel<G, NV, true, false><<<grid, 256, 0, h->stream>>>(h->m, bt, none, h->stats_d)
+#define CALL(G, NV) decode_kernel<G, NV, true, false, -1><<<grid, 256, 0, h->stream>>>(h->m, bt, none, h->stats_d)
     DISPATCH_LD(h->ld, CALL);
 #undef CALL
   } else {
-#define CALL(G, NV) decode_kernel<G, NV, false, false><<<grid, 256, 0, h->stream>>>(h->m, bt, none, h->stats_d)
+#define CALL(G, NV) decode_kernel<G, NV, false, false, -1><<<grid, 256, 0, h->stream>>>(h->m, bt, none, h->stats_d)
     DISPATCH_LD(h->ld, CALL);
 #undef CALL
   }
@@ -384,7 +403,10 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleA
     uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt);
     KERNEL_OK(h);
   }
-  if (h->world > 1) {
+  // CDAE_B200_DEBUG_SKIP_ALLREDUCE=1: measurement aid only (ranks diverge) — isolates the cost of
+  // the collective in a scaling run
+  static const bool skip_allreduce = getenv("CDAE_B200_DEBUG_SKIP_ALLREDUCE") != nullptr;
+  if (h->world > 1 && !skip_allreduce) {
     ProfScope ps(h, CDAE_K_ALLREDUCE);
     NC(g_nccl.AllReduce(h->grad.p, h->grad.p, h->grad_floats, kNcclFloat, kNcclSum,
                         (ncclComm_t)h->comm, h->stream));
@@ -478,7 +500,7 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   cdae_handle* h = new cdae_handle();
   h->cfg = *cfg;
   h->U = U; h->I = I; h->K = cfg->num_dim;
-  h->ld = (int)round_up(cfg->num_dim, 32);  // rows are whole 128-byte lines
+  h->ld = row_stride(cfg->num_dim);
   h->I4 = round_up(I, 4);
   h->nnz = row_ptr[U];
   h->batch_users = cfg->batch_users > 0 ? cfg->batch_users : 8192;

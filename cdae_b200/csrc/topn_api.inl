@@ -73,17 +73,19 @@ static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* us
   const int64_t n_pad = round_up(n_users, tc::TILE_U), I_pad = round_up(h->I, tc::TILE_I);
   TRY(ensure(h, h->tc_zb, (size_t)(n_pad * Kp)));
   TRY(ensure(h, h->tc_wb, (size_t)(I_pad * Kp)));
-  TRY(ensure(h, h->tc_wmax, (size_t)round_up(K + 1, 4)));
+  TRY(ensure(h, h->tc_wmax, (size_t)round_up(K + 2, 4)));
   TRY(ensure(h, h->tc_eps, (size_t)n_users));
   TRY(ensure(h, h->tc_thr, (size_t)n_users));
   TRY(ensure(h, h->tc_redo, (size_t)n_users + 1));
   int* redo_cnt = h->tc_redo.p + n_users;
-  CU(cudaMemsetAsync(h->tc_wmax.p, 0, sizeof(float) * (K + 1), h->stream));
+  CU(cudaMemsetAsync(h->tc_wmax.p, 0, sizeof(float) * (K + 2), h->stream));
   CU(cudaMemsetAsync(redo_cnt, 0, sizeof(int), h->stream));
   {
     ProfScope ps(h, CDAE_K_TOPN_PACK);
     tc::absmax_cols_kernel<<<std::min<int>(cdiv(h->I, 128), h->sm_count * 4), 256, 0, h->stream>>>(
         Wd, h->m.bp, h->I, K, h->ld, h->tc_wmax.p);
+    KERNEL_OK(h);
+    tc::rownorm_max_kernel<<<cdiv(h->I * 32, 256), 256, 0, h->stream>>>(Wd, h->I, K, h->ld, h->tc_wmax.p);
     KERNEL_OK(h);
     tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(
         Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, reinterpret_cast<__nv_bfloat16*>(h->tc_wb.p));

@@ -43,7 +43,7 @@ constexpr int CAND_MAX = 96;  // largest per-user candidate buffer
 __host__ __device__ constexpr int epi_warps(int kb) { return kb <= 3 ? 2 : 1; }
 // candidate slots per user (all buffers together): what is left of the 227 KB after A and B
 __host__ __device__ constexpr int cand_slots(int kb) {
-  return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? 48 : 40;
+  return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? 48 : 36;
 }
 __host__ __device__ constexpr int buf_slots(int kb) { return cand_slots(kb) / epi_warps(kb); }
 // a compaction keeps between keep_lo and keep_hi entries of a buffer
@@ -197,6 +197,22 @@ __global__ void __launch_bounds__(256) absmax_cols_kernel(const float* __restric
   }
 }
 
+// out[K+1] = max_i ||W'[i]||_2^2 (one warp per row), the Cauchy-Schwarz side of the error bound.
+__global__ void __launch_bounds__(256) rownorm_max_kernel(const float* __restrict__ W, int64_t I, int K, int ld,
+                                                          float* __restrict__ out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  if (r < I)
+    for (int k = lane; k < K; k += 32) {
+      const float v = W[r * ld + k];
+      s = fmaf(v, v, s);
+    }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0 && r < I) atomicMax(reinterpret_cast<int*>(out + K + 1), __float_as_int(s));
+}
+
 // Wb[i][0..K) = bf16(W'[i]), Wb[i][K] = bf16(b'[i]), Wb[i][K+1] = bf16(b'[i] - hi); rows >= I and
 // the remaining pad columns are 0.  One thread per (row, 8-column group).
 __global__ void __launch_bounds__(256) pack_w_bf16_kernel(const float* __restrict__ W, const float* __restrict__ bp,
@@ -227,9 +243,10 @@ __global__ void __launch_bounds__(256) pack_w_bf16_kernel(const float* __restric
 
 // Zb[r][0..K) = bf16(z of user r), Zb[r][K] = Zb[r][K+1] = 1; rows >= n are 0.  Also the per-user
 // error bound: approx = sum_k bf16(z_k) bf16(w_k) + bhi + blo accumulated in fp32 by the tensor core;
-//   |approx - exact| <= (2^-8 * 1.01 + (Kp + 2) * 2^-22) * sum_k |z_k| wmax_k   (operand rounding 2^-9
-//   each, product exact, fp32 accumulation)  +  (2^-16 + (Kp + 2) * 2^-22) * bmax   (bias residual).
-// One warp per user.
+//   |approx - exact| <= (2^-8 * 1.01 + (Kp + 2) * 2^-22) * S   (operand rounding 2^-9 each, product
+//   exact, fp32 accumulation)  +  (2^-16 + (Kp + 2) * 2^-22) * bmax   (bias residual), where
+//   S >= sum_k |z_k||w_ik| for every item i:  S = min( sum_k |z_k| max_i|w_ik| ,  ||z||_2 max_i||w_i||_2 ).
+// One warp per user.  wmax = [K column maxima | bmax | max row norm squared].
 __global__ void __launch_bounds__(256) pack_z_bf16_kernel(const float* __restrict__ Z, const int32_t* __restrict__ users,
                                                           int n, int64_t n_pad, int K, int ld, int Kp,
                                                           const float* __restrict__ wmax /*[K+1]*/,
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(256) pack_z_bf16_kernel(const float* __restric
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n_pad) return;
-  float acc = 0.f;
+  float acc = 0.f, zz = 0.f;
   const float* z = nullptr;
   if (r < n) z = Z + (int64_t)(users ? users[r] : r) * ld;
   for (int c = lane; c < Kp; c += 32) {
@@ -246,6 +263,7 @@ __global__ void __launch_bounds__(256) pack_z_bf16_kernel(const float* __restric
       if (c < K) {
         v = z[c];
         acc += fabsf(v) * wmax[c];
+        zz = fmaf(v, v, zz);
       } else if (c <= K + 1) {
         v = 1.f;
       }
@@ -253,10 +271,14 @@ __global__ void __launch_bounds__(256) pack_z_bf16_kernel(const float* __restric
     out[r * Kp + c] = __float2bfloat16_rn(v);
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  for (int off = 16; off > 0; off >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    zz += __shfl_xor_sync(0xffffffffu, zz, off);
+  }
   if (lane == 0 && r < n) {
     const float slack = (float)(Kp + 2) * 2.3841858e-7f;  // 2^-22
-    eps[r] = (0.00390625f * 1.01f + slack) * acc + (1.52587890625e-5f + slack) * wmax[K];
+    const float cs = sqrtf(zz) * sqrtf(wmax[K + 1]) * 1.0001f;  // Cauchy-Schwarz, rounded up
+    eps[r] = (0.00390625f * 1.01f + slack) * fminf(acc, cs) + (1.52587890625e-5f + slack) * wmax[K];
   }
 }
 
@@ -270,13 +292,17 @@ template <int C, int KEEP_LO, int KEEP_HI>
 __device__ __noinline__ void compact(float* bs, int* bi, int* cnt_io, float* thr_io) {
   int cnt = *cnt_io;
   float thr = *thr_io;
+  // all C slots are read unconditionally (independent loads, fully pipelined); slots >= cnt are
+  // masked to -inf so they never count
   float mn = INFINITY, hi = -INFINITY;
-  for (int e = 0; e < C; ++e)
+#pragma unroll 8
+  for (int e = 0; e < C; ++e) {
+    const float s = bs[e * TILE_U];
     if (e < cnt) {
-      const float s = bs[e * TILE_U];
       mn = fminf(mn, s);
       hi = fmaxf(hi, s);
     }
+  }
   const bool need = cnt > KEEP_HI;
   bool done = !need;
   // count(s > lo) > KEEP_HI  and  count(s > hi) = 0 < KEEP_LO
@@ -286,8 +312,8 @@ __device__ __noinline__ void compact(float* bs, int* bi, int* cnt_io, float* thr
     if (__all_sync(0xffffffffu, done)) break;
     const float mid = 0.5f * (lo + hi);
     int k = 0;
-    for (int e = 0; e < C; ++e)
-      if (e < cnt) k += bs[e * TILE_U] > mid;
+#pragma unroll 8
+    for (int e = 0; e < C; ++e) k += (e < cnt) & (bs[e * TILE_U] > mid);
     if (!done) {
       if (k > KEEP_HI) lo = mid;
       else if (k < KEEP_LO) hi = mid;
@@ -297,16 +323,16 @@ __device__ __noinline__ void compact(float* bs, int* bi, int* cnt_io, float* thr
   if (need && !done) tnew = hi;
   if (tnew > thr) {
     int w = 0;
-    for (int e = 0; e < C; ++e)
-      if (e < cnt) {
-        const float s = bs[e * TILE_U];
-        const int id = bi[e * TILE_U];
-        if (s > tnew) {
-          bs[w * TILE_U] = s;
-          bi[w * TILE_U] = id;
-          ++w;
-        }
+#pragma unroll 4
+    for (int e = 0; e < C; ++e) {
+      const float s = bs[e * TILE_U];
+      const int id = bi[e * TILE_U];
+      if (e < cnt && s > tnew) {
+        bs[w * TILE_U] = s;
+        bi[w * TILE_U] = id;
+        ++w;
       }
+    }
     cnt = w;
     thr = tnew;
   }
@@ -455,50 +481,65 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
     }
   } else if (warp < 4) {
     // ===== rated-item bitmaps: thread h owns rows h and h + 64 =====
+    // A cursor walks each user's ascending train row once per sweep.  `cur` is the next rated item,
+    // `nxt` the one after it, loaded one step AHEAD so that the tile loop never waits on a
+    // dependent global load (the first version did: ~2 L2 round trips per rated item made these
+    // two warps, not the MMA or the epilogue, the pace of the whole kernel — profiles/r01_c_*).
     const int h = threadIdx.x - 64;
-    int pos[2], end[2], nxt[2];
+    const int32_t* rowp[2];
+    int pos[2], end[2], cur[2], nxt[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int r = h + q * 64;
+      rowp[q] = a.col;
       pos[q] = end[q] = 0;
-      nxt[q] = 0x7fffffff;
+      cur[q] = nxt[q] = 0x7fffffff;
       if (u0 + r < a.n_users) {
         const int64_t uid = a.users ? a.users[u0 + r] : (u0 + r);
         const int64_t p0 = a.row_ptr[uid], p1 = a.row_ptr[uid + 1];
+        rowp[q] = a.col + p0;
         end[q] = (int)(p1 - p0);
-        if (end[q] > 0) nxt[q] = a.col[p0];
+        if (end[q] > 0) cur[q] = rowp[q][0];
+        if (end[q] > 1) nxt[q] = rowp[q][1];
       }
     }
     for (int t = 0; t < a.n_tiles; ++t) {
       const int buf = t & 1;
       mbar_wait(b_empty + buf, ((t >> 1) & 1) ^ 1);
-      const int64_t i0 = (int64_t)t * TILE_I;
+      const int i0 = t * TILE_I, i1 = i0 + TILE_I;
       uint32_t* my = bm + buf * 8 * TILE_U;
+      uint32_t w[2][8];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int r = h + q * 64;
-        uint32_t w[8];
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[q][c] = 0u;
+      if ((int64_t)i1 > a.I) {
+        // columns that are not items at all (the padded tail of the last tile)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          // columns that are not items at all (the padded tail of the last tile)
-          const int64_t first = i0 + c * 32;
-          w[c] = first + 32 <= a.I ? 0u : (first >= a.I ? 0xffffffffu : (0xffffffffu << (int)(a.I - first)));
+          const int64_t first = (int64_t)i0 + c * 32;
+          const uint32_t mask = first + 32 <= a.I ? 0u : (first >= a.I ? 0xffffffffu : (0xffffffffu << (int)(a.I - first)));
+          w[0][c] = w[1][c] = mask;
         }
-        if (nxt[q] < i0 + TILE_I) {
-          const int64_t uid = a.users ? a.users[u0 + r] : (u0 + r);
-          const int32_t* row = a.col + a.row_ptr[uid];
-          while (nxt[q] < i0 + TILE_I) {
-            const int rel = (int)(nxt[q] - i0);
+      }
+      while (cur[0] < i1 || cur[1] < i1) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (cur[q] < i1) {
+            const int rel = cur[q] - i0;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              if ((rel >> 5) == c) w[c] |= 1u << (rel & 31);
+              if ((rel >> 5) == c) w[q][c] |= 1u << (rel & 31);
+            cur[q] = nxt[q];
             ++pos[q];
-            nxt[q] = pos[q] < end[q] ? row[pos[q]] : 0x7fffffff;
+            nxt[q] = pos[q] + 1 < end[q] ? rowp[q][pos[q] + 1] : 0x7fffffff;
           }
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) my[c * TILE_U + r] = w[c];
       }
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) my[c * TILE_U + h + q * 64] = w[q][c];
       mbar_arrive(b_full + buf);
     }
   } else {
@@ -578,3 +619,6 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
 
 }  // namespace tc
 }  // namespace cdae
+static_assert(cdae::tc::smem_bytes(1) <= 232448 && cdae::tc::smem_bytes(2) <= 232448 && cdae::tc::smem_bytes(3) <= 232448 &&
+                  cdae::tc::smem_bytes(4) <= 232448 && cdae::tc::smem_bytes(5) <= 232448,
+              "topn_tc_kernel shared memory exceeds the 227 KB a CTA can opt into");

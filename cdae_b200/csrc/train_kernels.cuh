@@ -3,8 +3,10 @@
 // One frozen minibatch of users (SURVEY.md Appendix A "frozen-batch") runs as
 //   gather(+mask) -> activate -> decode(+negatives) -> hidden_backward -> scatter -> apply
 //
-// Layout: all item/user tables are row-major [rows][ld] fp32 with ld = round_up(K, 32): every
-// row is a whole number of 128-byte lines (pad columns are kept at exactly 0).  A row is owned
+// Layout: all item/user tables are row-major [rows][ld] fp32 with ld = a whole number of
+// 128-byte lines that one <G,NV> geometry covers EXACTLY (ld = 4*G*NV: 32, 64, 96, 128, 192, 256,
+// 384 or 512 floats, row_stride() in api.cu; pad columns are kept at exactly 0), so no kernel
+// needs a column bound check.  A row is owned
 // by a GROUP of G >= 8 lanes, each holding NV <= 4 float4 (column 4*(v*G+lane) .. +3), so ONE
 // warp-level 16-byte load/reduction covers whole 128-byte lines of 32/G rows.  History
 // (profiles/r01_*): v1 used 224-byte rows with 16 lanes per row and was issue-bound; v2 used 4
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        w[t][v] = (it[t] >= 0 && c < m.ld) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+        w[t][v] = it[t] >= 0 ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
       }
 #pragma unroll
     for (int t = 0; t < UNR; ++t)
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
   for (int v = 0; v < NV; ++v) {
     acc[v] = cross_group_sum<G>(acc[v]);
     const int c = RM::col4(gl, v);
-    if (grp == 0 && c < m.ld) red_add_v4(bt.H + (int64_t)wi.u_local * m.ld + c, acc[v]);
+    if (grp == 0) red_add_v4(bt.H + (int64_t)wi.u_local * m.ld + c, acc[v]);
   }
 }
 
@@ -257,9 +259,16 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
 // Tied weights and o in the corrupted input: the lambda term is left to scatter_kernel so the
 // row receives ONE lambda per merged occurrence (cdae.hpp:249-250, 342-343).
 // TRAIN=false scores the positives only and accumulates loss(y,1): CDAE::data_loss :93-96.
+#ifndef DECODE_MIN_BLOCKS
+#define DECODE_MIN_BLOCKS 3  // resident CTAs per SM the register allocation must allow (A/B: tools/ab_build.sh)
+#endif
 constexpr int DECODE_MAX_NEGS = 96;  // ch_out * num_neg <= 96 by construction (api.cu)
-template <int G, int NV, bool TRAIN, bool SAMPLED>
-__global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, SampleArgs sa,
+// LT >= 0 fixes the loss at compile time (CROSS_ENTROPY and SQUARE, the two that are meaningful for
+// CDAE): the 7-way switch of loss_grad() and its copies in the unrolled row loop
+// were ~25% of the executed instructions (BRA/BSSY/BSYNC/ISETP, profiles/r01_b_*).  LT = -1 reads
+// m.loss at run time.
+template <int G, int NV, bool TRAIN, bool SAMPLED, int LT>
+__global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS) decode_kernel(ModelDev m, BatchDev bt, SampleArgs sa,
                                                      StatsDev* stats) {
   using RM = RowMap<G, NV>;
   constexpr int NG = RM::NG, UNR = RM::UNR;
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, Sa
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c = RM::col4(gl, v);
-    z[v] = c < m.ld ? ld4(bt.Z + (int64_t)wi.u_local * m.ld + c) : f4zero();
+    z[v] = ld4(bt.Z + (int64_t)wi.u_local * m.ld + c);
     hg[v] = f4zero();
   }
   float loss_acc = 0.f;
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, Sa
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        w[t][v] = (it[t] >= 0 && c < m.ld) ? ld4(Wd + (int64_t)it[t] * m.ld + c) : f4zero();
+        w[t][v] = it[t] >= 0 ? ld4(Wd + (int64_t)it[t] * m.ld + c) : f4zero();
       }
       bp[t] = it[t] >= 0 ? __ldg(m.bp + it[t]) : 0.f;
     }
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, Sa
       const int r = base + t * NG + grp;
       const float truth = r < n ? 1.f : 0.f;
       float l;
-      const float g = loss_grad(m.loss, y[t] + bp[t], truth, &l, &bad);
+      const float g = loss_grad(LT >= 0 ? LT : m.loss, y[t] + bp[t], truth, &l, &bad);
       if (gl == 0) loss_acc += l;
       if (!TRAIN) continue;
       const float lam = merged[t] ? 0.f : m.lambda;
@@ -345,7 +354,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, Sa
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
         hg[v] = fma4(g, w[t][v], hg[v]);
-        if (c < m.ld) red_add_v4(gWd + (int64_t)it[t] * m.ld + c, fma4(g, z[v], scale4(lam, w[t][v])));
+        red_add_v4(gWd + (int64_t)it[t] * m.ld + c, fma4(g, z[v], scale4(lam, w[t][v])));
       }
       if (gl == 0) red_add_f32(m.gbp + it[t], g + m.lambda * bp[t]);
     }
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(256) decode_kernel(ModelDev m, BatchDev bt, Sa
     for (int v = 0; v < NV; ++v) {
       hg[v] = cross_group_sum<G>(hg[v]);
       const int c = RM::col4(gl, v);
-      if (grp == 0 && c < m.ld) red_add_v4(bt.HG + (int64_t)wi.u_local * m.ld + c, hg[v]);
+      if (grp == 0) red_add_v4(bt.HG + (int64_t)wi.u_local * m.ld + c, hg[v]);
     }
   }
   loss_acc = group_sum<32>(loss_acc);
@@ -446,9 +455,9 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c = RM::col4(gl, v);
-    d[v] = c < m.ld ? ld4(bt.D + (int64_t)wi.u_local * m.ld + c) : f4zero();
+    d[v] = ld4(bt.D + (int64_t)wi.u_local * m.ld + c);
     sd[v] = scale4(m.scale, d[v]);
-    if (m.linear_function && c < m.ld) sd[v] = mul4(ld4(m.Uu + (int64_t)wi.uid * m.ld + c), sd[v]);
+    if (m.linear_function) sd[v] = mul4(ld4(m.Uu + (int64_t)wi.uid * m.ld + c), sd[v]);
     gu[v] = f4zero();
   }
   for (int base = 0; base < wi.n; base += NG * UNR) {
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        w[t][v] = (it[t] >= 0 && c < m.ld) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+        w[t][v] = it[t] >= 0 ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
       }
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
@@ -472,7 +481,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        if (c < m.ld) red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, fma4(m.lambda, w[t][v], sd[v]));
+        red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, fma4(m.lambda, w[t][v], sd[v]));
         if (m.linear_function) gu[v] = add4(gu[v], mul4(d[v], w[t][v]));
       }
     }
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
     for (int v = 0; v < NV; ++v) {
       gu[v] = cross_group_sum<G>(gu[v]);
       const int c = RM::col4(gl, v);
-      if (grp == 0 && c < m.ld) red_add_v4(bt.GU + (int64_t)wi.u_local * m.ld + c, gu[v]);
+      if (grp == 0) red_add_v4(bt.GU + (int64_t)wi.u_local * m.ld + c, gu[v]);
     }
   }
 }

@@ -112,6 +112,7 @@ class CDAE:
             pass
 
     def init_params(self, seed):
+        self._topk = 0
         _lib.check(self._L.cdae_init_params(self._h, seed))
 
     # -- parameters -------------------------------------------------------------------------
@@ -121,6 +122,7 @@ class CDAE:
         return r.value, c.value
 
     def set_params(self, params):
+        self._topk = 0
         for k, v in params.items():
             r, c = self.param_shape(k)
             if r * c == 0:
@@ -150,6 +152,7 @@ class CDAE:
             _lib.check(self._L.cdae_train_epoch_csr(self._h, _ptr(rp, _lib.i64p), _ptr(cl, _lib.i32p),
                                                     seed, epoch, C.byref(st)))
         self.last_stats = st
+        self._topk = 0                  # stored lists are stale
         return st
 
     def train_users(self, uids, keep_mask, negatives):
@@ -161,6 +164,7 @@ class CDAE:
         _lib.check(self._L.cdae_train_users(self._h, _ptr(u, _lib.i64p), len(u), _ptr(k, _lib.u8p),
                                             _ptr(n, _lib.i32p), C.byref(st)))
         self.last_stats = st
+        self._topk = 0
         return st
 
     def train_one_user_corruption(self, uid, input_items, negatives):
