@@ -172,7 +172,7 @@ def run_reference(args):
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -308,7 +308,7 @@ def run_ours(args):
             info["value"] = v
             info["unit"] = UNIT
             line["cpu_baseline"] = info
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -341,7 +341,31 @@ def topn_section(m, U, peak_tf, peak_src):
     return out
 
 
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints
+    "NCCL version ..." from C code at communicator init), so file descriptor 1 is pointed at stderr
+    for the whole run and the JSON line goes to the saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+
+OUT = None
+
+
+def emit(obj):
+    OUT.emit(json.dumps(obj))
+
+
 def main():
+    global OUT
+    OUT = OneLineStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

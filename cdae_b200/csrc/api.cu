@@ -278,6 +278,7 @@ static BatchDev make_batch(cdae_handle* h, const WorkItem* in, int64_t n_in, con
   bt.keep = h->keep.p; bt.negs = h->negs.p;
   bt.H = h->acc3.p; bt.HG = h->acc3.p + per; bt.GU = h->acc3.p + 2 * per;
   bt.Z = h->zd.p; bt.D = h->zd.p + per;
+  bt.flags = 0;
   return bt;
 }
 

@@ -292,25 +292,30 @@ template <int C, int KEEP_LO, int KEEP_HI>
 __device__ __noinline__ void compact(float* bs, int* bi, int* cnt_io, float* thr_io) {
   int cnt = *cnt_io;
   float thr = *thr_io;
-  // all C slots are read unconditionally (independent loads, fully pipelined); slots >= cnt are
-  // masked to -inf so they never count
-  float mn = INFINITY, hi = -INFINITY;
+  // all C slots are read unconditionally (independent loads, pipelined); slots >= cnt are masked
+  float mn = INFINITY, hi = -INFINITY, sum = 0.f;
 #pragma unroll 8
   for (int e = 0; e < C; ++e) {
     const float s = bs[e * TILE_U];
     if (e < cnt) {
       mn = fminf(mn, s);
       hi = fmaxf(hi, s);
+      sum += s;
     }
   }
   const bool need = cnt > KEEP_HI;
   bool done = !need;
-  // count(s > lo) > KEEP_HI  and  count(s > hi) = 0 < KEEP_LO
+  // bracket: count(s > lo) > KEEP_HI  and  count(s > hi) = 0 < KEEP_LO
   float lo = (thr == -INFINITY) ? mn - 1.f : thr;
   float tnew = thr;
-  for (int it = 0; it < 26; ++it) {
+  // First pivot: the entries are the upper tail of the score distribution above `lo`, roughly
+  // exponential with mean excess (mean - lo), so a fraction f survives a cut at
+  // lo + (mean - lo) * ln(1/f); aim at the middle of the keep window.  Then plain bisection.
+  const float f = 0.5f * (float)(KEEP_LO + KEEP_HI) / (float)max(cnt, 1);
+  float mid = lo + (sum / (float)max(cnt, 1) - lo) * __logf(1.f / f);
+  if (!(mid > lo && mid < hi)) mid = 0.5f * (lo + hi);
+  for (int it = 0; it < 28; ++it) {
     if (__all_sync(0xffffffffu, done)) break;
-    const float mid = 0.5f * (lo + hi);
     int k = 0;
 #pragma unroll 8
     for (int e = 0; e < C; ++e) k += (e < cnt) & (bs[e * TILE_U] > mid);
@@ -319,6 +324,7 @@ __device__ __noinline__ void compact(float* bs, int* bi, int* cnt_io, float* thr
       else if (k < KEEP_LO) hi = mid;
       else { tnew = mid; done = true; }
     }
+    mid = 0.5f * (lo + hi);
   }
   if (need && !done) tnew = hi;
   if (tnew > thr) {
@@ -391,6 +397,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
                                                                  const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   constexpr int C = cand_slots(KB), EPI = epi_warps(KB), C2 = buf_slots(KB);
   constexpr int KEEP_LO = keep_lo(KB), KEEP_HI = keep_hi(KB);
+  constexpr int SOFT = (C2 - KEEP_HI) / 2;   // ask for the shared compaction when fewer slots are free
   static_assert(KEEP_HI <= C2 - 8 && KEEP_LO >= 10 && KEEP_LO < KEEP_HI, "candidate buffer geometry");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -401,7 +408,8 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
   uint32_t* bm = reinterpret_cast<uint32_t*>(ci + C * TILE_U);     // [2][8][128]
   int* mcnt = reinterpret_cast<int*>(bm + 2 * 8 * TILE_U);          // [2][128] final counts per buffer
   float* mthr = reinterpret_cast<float*>(mcnt + 2 * TILE_U);        // [2][128] final thresholds
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mthr + 2 * TILE_U);
+  volatile int* creq = reinterpret_cast<volatile int*>(mthr + 2 * TILE_U);  // [2] tile that asked for a compaction
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mthr + 2 * TILE_U + 2);
   uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA -> TMA
   uint64_t* a_full = bars + 2 * NSTAGE;  // A tile landed
@@ -433,6 +441,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x == 0) creq[0] = creq[1] = -1;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -583,6 +592,13 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         mbar_arrive(t_empty + buf);
         mbar_arrive(b_empty + buf);
       }
+      // Compactions are taken TOGETHER by all epilogue warps at a tile boundary: a compaction costs
+      // about as much as scanning a whole tile, and with only two accumulator buffers a warp
+      // that compacts on its own stalls the MMA and, through it, the seven other warps — ~150
+      // separate stalls per sweep in the first version (profiles/r01_c_*), ~25 shared ones now.
+      if (cnt > C2 - SOFT) creq[t & 1] = t;
+      named_bar_sync(2, 128 * EPI);
+      if (creq[t & 1] == t) compact<C2, KEEP_LO, KEEP_HI>(bs, bi, &cnt, &thr);
     }
     // ---- merge the buffers of the warp pair and write the candidates out
     mcnt[hf * TILE_U + row] = cnt;

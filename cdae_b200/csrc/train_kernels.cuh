@@ -47,7 +47,10 @@ struct BatchDev {
   uint8_t* keep;              // [minibatch slots]       1 = input item survives corruption
   const int32_t* negs;        // [minibatch slots * nu]  explicit negatives (unsampled mode only)
   float *H, *Z, *HG, *D, *GU;  // [n_users][ld]
+  int flags;                  // BATCH_BY_UID: rows of H / Z are indexed by GLOBAL uid (whole-table
+                              // encode); BATCH_KEEP_ALL: no corruption mask, every input item is kept
 };
+enum { BATCH_BY_UID = 1, BATCH_KEEP_ALL = 2 };
 
 // Counter-based sampling parameters (same specification as oracle/cdae_oracle.h).
 struct SampleArgs {
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
       atomicAdd(&stats->inputs_kept[warp % STAT_STRIPES], (unsigned long long)kept);
     __syncwarp();  // the mask bytes written above are read by other lanes below
   }
+  const bool keep_all = !SAMPLED && (bt.flags & BATCH_KEEP_ALL);
   float4 acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = f4zero();
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
       const int r = base + t * NG + grp;
-      it[t] = (r < wi.n && keep[r]) ? __ldg(items + r) : -1;
+      it[t] = (r < wi.n && (keep_all || keep[r])) ? __ldg(items + r) : -1;
     }
     float4 w[UNR][NV];
 #pragma unroll
@@ -223,11 +227,12 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[v] = add4(acc[v], w[t][v]);
   }
+  const int64_t hrow = (bt.flags & BATCH_BY_UID) ? (int64_t)wi.uid : (int64_t)wi.u_local;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     acc[v] = cross_group_sum<G>(acc[v]);
     const int c = RM::col4(gl, v);
-    if (grp == 0) red_add_v4(bt.H + (int64_t)wi.u_local * m.ld + c, acc[v]);
+    if (grp == 0) red_add_v4(bt.H + hrow * m.ld + c, acc[v]);
   }
 }
 
@@ -238,7 +243,8 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
   if (idx >= (int64_t)bt.n_users * ld4n) return;
   const int u = (int)(idx / ld4n), c = (int)(idx % ld4n) * 4;
   const int64_t uid = bt.uids[u];
-  float4 h = scale4(scale, ld4(bt.H + (int64_t)u * m.ld + c));
+  const int64_t zrow = (bt.flags & BATCH_BY_UID) ? uid : (int64_t)u;
+  float4 h = scale4(scale, ld4(bt.H + zrow * m.ld + c));
   if (m.linear_function) h = mul4(ld4(m.Uu + uid * m.ld + c), h);
   h = add4(h, ld4(m.b + c));
   if (m.user_factor) h = add4(h, ld4(m.Wu + uid * m.ld + c));
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
     if (!m.linear) x[i] = m.tanh_act ? act_tanh(x[i]) : act_sigmoid(x[i]);
     if (c + i >= m.K) x[i] = 0.f;
   }
-  st4(bt.Z + (int64_t)u * m.ld + c, make_float4(x[0], x[1], x[2], x[3]));
+  st4(bt.Z + zrow * m.ld + c, make_float4(x[0], x[1], x[2], x[3]));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -29,6 +29,9 @@ def run(U, I, K, mean, seed=3):
         out[path] = (ids, sc, m.topn_stats(), dt, prof)
         m.close()
     same = (out["fp32"][0] == out["tc"][0]).all(axis=1)
+    tc_ms = out["tc"][4]["topn"][0]
+    print("   tensor path: %.1f TFLOP/s algorithmic (2*U*I*K), %.1f executed (padded K)"
+          % (2.0 * U * I * K / tc_ms / 1e9, 2.0 * U * I * ((K + 2 + 63) // 64 * 64) / tc_ms / 1e9), flush=True)
     print("U=%d I=%d K=%d: identical lists %d/%d  tc stats(path,verified,redone)=%s  first-call wall fp32 %.3fs tc %.3fs"
           % (U, I, K, same.sum(), U, out["tc"][2], out["fp32"][3], out["tc"][3]), flush=True)
     for p in ("fp32", "tc"):
@@ -46,5 +49,9 @@ if __name__ == "__main__":
         ok &= run(*args)
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         ok &= run(100000, 50000, 50, 30.0)
+    if len(sys.argv) > 1 and sys.argv[1] == "shapes":      # BASELINE.json configs C, D (one rank), E (one rank)
+        ok &= run(20000, 27000, 200, 145.0)
+        ok &= run(125000, 200000, 100, 30.0)
+        ok &= run(62500, 100000, 256, 50.0)
     print("tc_probe:", "ok" if ok else "MISMATCH")
     sys.exit(0 if ok else 1)
