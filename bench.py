@@ -330,7 +330,7 @@ def topn_section(m, U, peak_tf, peak_src):
     alg = 2.0 * U * ITEMS * K                                  # 2*I*K flops per user
     out = {"what": "CDAE::recommend, all users x all items, top-10 (cdae_topn_build)",
            "path": "tcgen05 bf16 + exact fp64 re-rank" if path == 1 else "fp32 CUDA cores",
-           "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank")) / reps / 1e3),
+           "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank", "topn_exact")) / reps / 1e3),
            "candidate_kernel_ms": ms, "verified_users": verified, "redone_exact_users": redone,
            "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel<%d>" % (kp // 64),
                         "achieved": alg / (ms / 1e3) / 1e12 if ms > 0 else None, "peak": peak_tf,

@@ -76,7 +76,7 @@ SIGNATURES = {
 }
 
 KERNEL_CLASSES = ["sample", "gather", "activate", "decode", "hidden_bwd", "scatter", "allreduce",
-                  "apply", "topn", "topn_pack", "topn_rerank"]
+                  "apply", "topn", "topn_pack", "topn_rerank", "topn_exact"]
 
 _lib = None
 

@@ -593,7 +593,7 @@ int cdae_destroy(cdae_handle* h) {
   h->cand_id.release(); h->cand_cnt.release(); h->cand_s.release(); h->flag_d.release();
   h->test_rp_d.release(); h->test_col_d.release();
   h->tc_zb.release(); h->tc_wb.release(); h->tc_wmax.release(); h->tc_eps.release();
-  h->tc_thr.release(); h->tc_redo.release();
+  h->tc_thr.release(); h->tc_redo.release(); h->tc_redo_thr.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -955,7 +955,7 @@ static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users
     CU(cudaFuncSetAttribute(topn_tile_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  ProfScope ps(h, CDAE_K_TOPN);
+  ProfScope ps(h, CDAE_K_TOPN_EXACT);
   topn_tile_fp32_kernel<<<cdiv(n_users, TT_U), 256, dyn, h->stream>>>(
       h->topn_z.p, Wd, h->m.bp, h->I, h->ld, users, (int)n_users, h->row_ptr_d.p, h->col_d.p,
       h->cand_id.p, h->cand_s.p, h->cand_cnt.p);

@@ -88,7 +88,10 @@ struct cdae_handle {
   // tensor-core candidate path (topn_tc.cuh)
   cdae::DevBuf<uint16_t> tc_zb, tc_wb;   // bf16 operands [rows_pad][Kp]
   cdae::DevBuf<float> tc_wmax, tc_eps, tc_thr;
-  cdae::DevBuf<int32_t> tc_redo;         // [n_users] + 1 counter at the end
+  cdae::DevBuf<int32_t> tc_redo;         // [unproven after sweep 1 | after sweep 2 | counter]
+  cdae::DevBuf<float> tc_redo_thr;       // start threshold of each user of sweep 2
+  const int32_t* tc_exact_list = nullptr;  // users left for the exact kernel (inside tc_redo)
+  int64_t topn_pass2_users = 0;          // users that needed the second tensor sweep
   int64_t topn_tc_users = 0, topn_redo_users = 0;  // last cdae_topn_build: verified on the tensor path / redone exactly
   int topn_path = 0;                     // 0 fp32 CUDA cores, 1 tcgen05
   cdae::DevBuf<int64_t> test_rp_d;

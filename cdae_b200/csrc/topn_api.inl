@@ -66,31 +66,18 @@ static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& m
   return 0;
 }
 
-// Candidates + verified exact lists for the users the bound proves; *n_redo users are left in
-// h->tc_redo for the exact path.
-static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users,
-                              int topk, int* n_redo) {
+// One sweep of the tensor-core candidate kernel over `n_users` users (`users` = their global ids, or
+// nullptr for 0..n-1) followed by the verifying re-rank.  Users whose list the bound cannot prove
+// are written to redo_list[0 .. *n_redo) together with a start threshold for a second sweep.
+// Wb (the packed item side) must already be in h->tc_wb; init_thr is nullable.
+static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users, int topk,
+                   const float* init_thr, int32_t* redo_list, float* redo_thr, int* redo_cnt, int* n_redo) {
   const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
   const int64_t n_pad = round_up(n_users, tc::TILE_U), I_pad = round_up(h->I, tc::TILE_I);
   TRY(ensure(h, h->tc_zb, (size_t)(n_pad * Kp)));
-  TRY(ensure(h, h->tc_wb, (size_t)(I_pad * Kp)));
-  TRY(ensure(h, h->tc_wmax, (size_t)round_up(K + 2, 4)));
-  TRY(ensure(h, h->tc_eps, (size_t)n_users));
-  TRY(ensure(h, h->tc_thr, (size_t)n_users));
-  TRY(ensure(h, h->tc_redo, (size_t)n_users + 1));
-  int* redo_cnt = h->tc_redo.p + n_users;
-  CU(cudaMemsetAsync(h->tc_wmax.p, 0, sizeof(float) * (K + 2), h->stream));
   CU(cudaMemsetAsync(redo_cnt, 0, sizeof(int), h->stream));
   {
     ProfScope ps(h, CDAE_K_TOPN_PACK);
-    tc::absmax_cols_kernel<<<std::min<int>(cdiv(h->I, 128), h->sm_count * 4), 256, 0, h->stream>>>(
-        Wd, h->m.bp, h->I, K, h->ld, h->tc_wmax.p);
-    KERNEL_OK(h);
-    tc::rownorm_max_kernel<<<cdiv(h->I * 32, 256), 256, 0, h->stream>>>(Wd, h->I, K, h->ld, h->tc_wmax.p);
-    KERNEL_OK(h);
-    tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(
-        Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, reinterpret_cast<__nv_bfloat16*>(h->tc_wb.p));
-    KERNEL_OK(h);
     tc::pack_z_bf16_kernel<<<cdiv(n_pad * 32, 256), 256, 0, h->stream>>>(
         h->topn_z.p, users, (int)n_users, n_pad, K, h->ld, Kp, h->tc_wmax.p,
         reinterpret_cast<__nv_bfloat16*>(h->tc_zb.p), h->tc_eps.p);
@@ -103,6 +90,7 @@ static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* us
   a.n_users = (int)n_users; a.I = h->I; a.n_tiles = (int)(I_pad / tc::TILE_I);
   a.users = users; a.row_ptr = h->row_ptr_d.p; a.col = h->col_d.p;
   a.cand_id = h->cand_id.p; a.cand_s = h->cand_s.p; a.cand_cnt = h->cand_cnt.p; a.cand_thr = h->tc_thr.p;
+  a.init_thr = init_thr;
   const int grid = (int)(n_pad / tc::TILE_U);
   {
     ProfScope ps(h, CDAE_K_TOPN);
@@ -119,11 +107,56 @@ static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* us
     ProfScope ps(h, CDAE_K_TOPN_RERANK);
     topn_rerank_kernel<<<cdiv(n_users, 8), 256, 0, h->stream>>>(
         h->topn_z.p, Wd, h->m.bp, h->K, h->ld, users, (int)n_users, h->cand_id.p, h->cand_cnt.p, tc::CAND_MAX,
-        topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, h->tc_thr.p, h->tc_eps.p, h->tc_redo.p, redo_cnt);
+        topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, h->tc_thr.p, h->tc_eps.p, redo_list, redo_cnt,
+        redo_thr);
     KERNEL_OK(h);
   }
   CU(cudaMemcpyAsync(n_redo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Tensor-core candidate phase: sweep 1 over all users from thr = -inf; sweep 2 over the (few)
+// users it could not prove, starting at the threshold sweep 1 derived for each of them, which
+// normally leaves only a handful of items above it; what is still unproven goes to the exact
+// fp32 kernel (*n_redo users, ids in h->tc_redo).
+static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users,
+                              int topk, int* n_redo) {
+  const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK);
+  const int64_t I_pad = round_up(h->I, tc::TILE_I);
+  TRY(ensure(h, h->tc_wb, (size_t)(I_pad * Kp)));
+  TRY(ensure(h, h->tc_wmax, (size_t)round_up(K + 2, 4)));
+  TRY(ensure(h, h->tc_eps, (size_t)n_users));
+  TRY(ensure(h, h->tc_thr, (size_t)n_users));
+  // [ids sweep 1 | ids sweep 2 | counter] and the matching start thresholds
+  TRY(ensure(h, h->tc_redo, (size_t)(2 * n_users + 4)));
+  TRY(ensure(h, h->tc_redo_thr, (size_t)n_users));
+  int32_t* redo1 = h->tc_redo.p;
+  int32_t* redo2 = h->tc_redo.p + n_users;
+  int* redo_cnt = h->tc_redo.p + 2 * n_users;
+  CU(cudaMemsetAsync(h->tc_wmax.p, 0, sizeof(float) * (K + 2), h->stream));
+  {
+    ProfScope ps(h, CDAE_K_TOPN_PACK);
+    tc::absmax_cols_kernel<<<std::min<int>(cdiv(h->I, 128), h->sm_count * 4), 256, 0, h->stream>>>(
+        Wd, h->m.bp, h->I, K, h->ld, h->tc_wmax.p);
+    KERNEL_OK(h);
+    tc::rownorm_max_kernel<<<cdiv(h->I * 32, 256), 256, 0, h->stream>>>(Wd, h->I, K, h->ld, h->tc_wmax.p);
+    KERNEL_OK(h);
+    tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(
+        Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, reinterpret_cast<__nv_bfloat16*>(h->tc_wb.p));
+    KERNEL_OK(h);
+  }
+  int n1 = 0;
+  TRY(tc_pass(h, Wd, users, n_users, topk, nullptr, redo1, h->tc_redo_thr.p, redo_cnt, &n1));
+  h->topn_pass2_users = n1;
+  *n_redo = n1;
+  h->tc_exact_list = redo1;
+  if (n1 > 0) {
+    int n2 = 0;
+    TRY(tc_pass(h, Wd, redo1, n1, topk, h->tc_redo_thr.p, redo2, nullptr, redo_cnt, &n2));
+    *n_redo = n2;
+    h->tc_exact_list = redo2;
+  }
   return 0;
 }
 
@@ -161,7 +194,7 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
     h->topn_path = 1;
     h->topn_tc_users = n_users - n_redo;
     h->topn_redo_users = n_redo;
-    exact_users = h->tc_redo.p;
+    exact_users = h->tc_exact_list;
     n_exact = n_redo;
   }
   if (n_exact > 0) {
@@ -169,7 +202,7 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
     ProfScope ps(h, CDAE_K_TOPN_RERANK);
     topn_rerank_kernel<<<cdiv(n_exact, 8), 256, 0, h->stream>>>(
         h->topn_z.p, Wd, h->m.bp, h->K, h->ld, exact_users, (int)n_exact, h->cand_id.p, h->cand_cnt.p, TOPN_M,
-        topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, nullptr, nullptr, nullptr, nullptr);
+        topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, nullptr, nullptr, nullptr, nullptr, nullptr);
     KERNEL_OK(h);
   }
   h->topn_ids_h.resize((size_t)(h->U * topk));

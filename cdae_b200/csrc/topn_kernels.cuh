@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
     int ld, const int32_t* __restrict__ users, int n_users, const int* __restrict__ cand_id,
     const int* __restrict__ cand_cnt, int stride, int topk, int32_t* __restrict__ out_id,
     float* __restrict__ out_s, int* __restrict__ short_flag, const float* __restrict__ thr,
-    const float* __restrict__ eps, int32_t* __restrict__ redo_list, int* __restrict__ redo_cnt) {
+    const float* __restrict__ eps, int32_t* __restrict__ redo_list, int* __restrict__ redo_cnt,
+    float* __restrict__ redo_thr) {
   __shared__ double sc[8][RERANK_MAX];
   __shared__ int ids[8][RERANK_MAX];
   __shared__ double kth[8];
@@ -178,7 +179,11 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
   __syncwarp();
   if (cnt < topk) {
     if (thr) {
-      if (lane == 0) redo_list[atomicAdd(redo_cnt, 1)] = (int32_t)uid;
+      if (lane == 0) {
+        const int slot = atomicAdd(redo_cnt, 1);
+        redo_list[slot] = (int32_t)uid;
+        if (redo_thr) redo_thr[slot] = -INFINITY;
+      }
       return;
     }
     if (lane == 0) *short_flag = 1;
@@ -209,7 +214,17 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
   if (thr) {
     const bool ok = (double)thr[u] + (double)eps[u] < kth[w];
     if (!ok) {
-      if (lane == 0) redo_list[atomicAdd(redo_cnt, 1)] = (int32_t)uid;
+      if (lane == 0) {
+        const int slot = atomicAdd(redo_cnt, 1);
+        redo_list[slot] = (int32_t)uid;
+        // An item of the true top-k has exact score >= kth (k candidates already reach it), hence
+        // approximate score >= kth - eps: a second sweep may START at a threshold just below that
+        // and then collects every possible member (rounded down, with a relative margin).
+        if (redo_thr) {
+          const double t0 = kth[w] - (double)eps[u];
+          redo_thr[slot] = __double2float_rd(t0 - 1e-6 * fabs(t0) - 1e-30);
+        }
+      }
       return;
     }
   }

@@ -358,6 +358,8 @@ struct TcArgs {
   float* cand_s;               // [n_users][CAND_MAX]  approximate scores
   int* cand_cnt;               // [n_users]
   float* cand_thr;             // [n_users]  final threshold (every non-candidate has approx <= thr)
+  const float* init_thr;       // nullable [n_users]: start threshold of each user (second pass: the
+                               // first pass proved that nothing at or below it can be in the top-k)
 };
 
 // One 32-column chunk of one accumulator tile for this thread's user: fast reject by the chunk
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
     const int row = q * 32 + lane;
     float* bs = cs + hf * C2 * TILE_U + row;   // entry e at bs[e * 128]
     int* bi = ci + hf * C2 * TILE_U + row;
-    float thr = -INFINITY;
+    float thr = (a.init_thr && u0 + row < a.n_users) ? a.init_thr[u0 + row] : -INFINITY;
     int cnt = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int NCH = 8 / EPI;            // chunks per tile for this warp

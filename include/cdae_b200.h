@@ -189,8 +189,8 @@ int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl
  * the summed milliseconds and the number of launches since cdae_profile(h, 1). */
 enum cdae_kernel_class {
   CDAE_K_SAMPLE = 0, CDAE_K_GATHER, CDAE_K_ACTIVATE, CDAE_K_DECODE, CDAE_K_HIDDEN_BWD,
-  CDAE_K_SCATTER, CDAE_K_ALLREDUCE, CDAE_K_APPLY, CDAE_K_TOPN /* candidate kernel */,
-  CDAE_K_TOPN_PACK, CDAE_K_TOPN_RERANK, CDAE_K_COUNT
+  CDAE_K_SCATTER, CDAE_K_ALLREDUCE, CDAE_K_APPLY, CDAE_K_TOPN /* tcgen05 candidate kernel */,
+  CDAE_K_TOPN_PACK, CDAE_K_TOPN_RERANK, CDAE_K_TOPN_EXACT /* fp32 candidate kernel */, CDAE_K_COUNT
 };
 int cdae_profile(cdae_handle* h, int32_t enable);
 int cdae_profile_get(cdae_handle* h, double* ms_out /*[CDAE_K_COUNT]*/,

@@ -29,7 +29,7 @@ def run(U, I, K, mean, seed=3):
         out[path] = (ids, sc, m.topn_stats(), dt, prof)
         m.close()
     same = (out["fp32"][0] == out["tc"][0]).all(axis=1)
-    tc_ms = out["tc"][4]["topn"][0]
+    tc_ms = out["tc"][4]["topn"][0] or 1e-9
     print("   tensor path: %.1f TFLOP/s algorithmic (2*U*I*K), %.1f executed (padded K)"
           % (2.0 * U * I * K / tc_ms / 1e9, 2.0 * U * I * ((K + 2 + 63) // 64 * 64) / tc_ms / 1e9), flush=True)
     print("U=%d I=%d K=%d: identical lists %d/%d  tc stats(path,verified,redone)=%s  first-call wall fp32 %.3fs tc %.3fs"
