@@ -55,7 +55,8 @@ static bool tc_path_wanted(cdae_handle* h, int topk) {
 }
 
 template <int KB>
-static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const tc::TcArgs& a, int grid) {
+static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const tc::TcArgs& a, int grid_x) {
+  const dim3 grid(grid_x, a.n_splits);
   static bool attr_set = false;
   const size_t dyn = tc::smem_bytes(KB);
   if (!attr_set) {
@@ -92,6 +93,16 @@ static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_
   a.cand_id = h->cand_id.p; a.cand_s = h->cand_s.p; a.cand_cnt = h->cand_cnt.p; a.cand_thr = h->tc_thr.p;
   a.init_thr = init_thr;
   const int grid = (int)(n_pad / tc::TILE_U);
+  // Item ranges: a sweep that starts from known thresholds (init_thr) is paced by the MMA, not by
+  // candidate handling, and has few user tiles — cut the items into ranges while the grid still fits one wave.
+  int S = 1;
+  if (init_thr) while (S < 8 && grid * S * 2 <= h->sm_count && a.n_tiles / (S * 2) >= 8) S *= 2;
+  a.n_splits = S;
+  a.tiles_per_split = (a.n_tiles + S - 1) / S;
+  a.seg = tc::CAND_MAX / S;
+  TRY(ensure(h, h->cand_cnt, (size_t)(n_users * S)));
+  TRY(ensure(h, h->tc_thr, (size_t)(n_users * S)));
+  a.cand_cnt = h->cand_cnt.p; a.cand_thr = h->tc_thr.p;
   {
     ProfScope ps(h, CDAE_K_TOPN);
     switch (KB) {
@@ -106,7 +117,7 @@ static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_
   {
     ProfScope ps(h, CDAE_K_TOPN_RERANK);
     topn_rerank_kernel<<<cdiv(n_users, 8), 256, 0, h->stream>>>(
-        h->topn_z.p, Wd, h->m.bp, h->K, h->ld, users, (int)n_users, h->cand_id.p, h->cand_cnt.p, tc::CAND_MAX,
+        h->topn_z.p, Wd, h->m.bp, h->K, h->ld, users, (int)n_users, h->cand_id.p, h->cand_cnt.p, a.seg, S,
         topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, h->tc_thr.p, h->tc_eps.p, redo_list, redo_cnt,
         redo_thr);
     KERNEL_OK(h);
@@ -201,7 +212,7 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
     TRY(topn_candidates(h, Wd, exact_users, n_exact));
     ProfScope ps(h, CDAE_K_TOPN_RERANK);
     topn_rerank_kernel<<<cdiv(n_exact, 8), 256, 0, h->stream>>>(
-        h->topn_z.p, Wd, h->m.bp, h->K, h->ld, exact_users, (int)n_exact, h->cand_id.p, h->cand_cnt.p, TOPN_M,
+        h->topn_z.p, Wd, h->m.bp, h->K, h->ld, exact_users, (int)n_exact, h->cand_id.p, h->cand_cnt.p, TOPN_M, 1,
         topk, h->topn_ids.p, h->topn_scores.p, h->flag_d.p, nullptr, nullptr, nullptr, nullptr, nullptr);
     KERNEL_OK(h);
   }

@@ -155,7 +155,7 @@ constexpr int RERANK_MAX = 96;
 __global__ void __launch_bounds__(256) topn_rerank_kernel(
     const float* __restrict__ Z, const float* __restrict__ Wd, const float* __restrict__ bp, int K,
     int ld, const int32_t* __restrict__ users, int n_users, const int* __restrict__ cand_id,
-    const int* __restrict__ cand_cnt, int stride, int topk, int32_t* __restrict__ out_id,
+    const int* __restrict__ cand_cnt, int stride, int n_splits, int topk, int32_t* __restrict__ out_id,
     float* __restrict__ out_s, int* __restrict__ short_flag, const float* __restrict__ thr,
     const float* __restrict__ eps, int32_t* __restrict__ redo_list, int* __restrict__ redo_cnt,
     float* __restrict__ redo_thr) {
@@ -166,15 +166,42 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
   const int u = blockIdx.x * 8 + w;
   if (u >= n_users) return;
   const int64_t uid = users ? users[u] : u;
-  const int cnt = cand_cnt[u];
   const float* z = Z + uid * ld;
-  for (int c = lane; c < cnt; c += 32) {
-    const int it = cand_id[(int64_t)u * stride + c];
-    const float* wr = Wd + (int64_t)it * ld;
-    double s = 0.;
-    for (int k = 0; k < K; ++k) s += (double)wr[k] * (double)z[k];
-    sc[w][c] = s + (double)bp[it];
-    ids[w][c] = it;
+  // candidates arrive in n_splits segments of `stride` slots (one per item range of the
+  // tensor-core kernel; a single segment otherwise); gather their ids, then score them exactly:
+  // 8 lanes per candidate read its row with 16-byte loads (4 candidates per warp step), partial
+  // dot products in fp64, 3 shuffles.  The summation order differs from a serial loop only in
+  // fp64 rounding (~1e-16 relative), far below any score gap fp32 parameters can form.
+  int cnt = 0;
+  float thr_u = -INFINITY;
+  for (int sgm = 0; sgm < n_splits; ++sgm) {
+    const int64_t slot = (int64_t)u * n_splits + sgm;
+    const int n = min(cand_cnt[slot], RERANK_MAX - cnt);
+    for (int c = lane; c < n; c += 32) ids[w][cnt + c] = cand_id[slot * stride + c];
+    cnt += n;
+    if (thr) thr_u = fmaxf(thr_u, thr[slot]);
+  }
+  __syncwarp();
+  {
+    const int grp = lane >> 3, gl = lane & 7;
+    for (int c0 = 0; c0 < cnt; c0 += 4) {
+      const int c = c0 + grp;
+      const int it = c < cnt ? ids[w][c] : -1;
+      double s = 0.;
+      if (it >= 0) {
+        const float* wr = Wd + (int64_t)it * ld;
+        for (int k = gl * 4; k < ld; k += 32) {   // pad columns of both rows are exactly 0
+          const float4 a = *reinterpret_cast<const float4*>(wr + k);
+          const float4 b = *reinterpret_cast<const float4*>(z + k);
+          s += (double)a.x * (double)b.x + (double)a.y * (double)b.y + (double)a.z * (double)b.z +
+               (double)a.w * (double)b.w;
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (gl == 0 && it >= 0) sc[w][c] = s + (double)bp[it];
+    }
   }
   __syncwarp();
   if (cnt < topk) {
@@ -212,7 +239,7 @@ __global__ void __launch_bounds__(256) topn_rerank_kernel(
   }
   __syncwarp();
   if (thr) {
-    const bool ok = (double)thr[u] + (double)eps[u] < kth[w];
+    const bool ok = (double)thr_u + (double)eps[u] < kth[w];
     if (!ok) {
       if (lane == 0) {
         const int slot = atomicAdd(redo_cnt, 1);

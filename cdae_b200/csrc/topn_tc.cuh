@@ -360,6 +360,9 @@ struct TcArgs {
   float* cand_thr;             // [n_users]  final threshold (every non-candidate has approx <= thr)
   const float* init_thr;       // nullable [n_users]: start threshold of each user (second pass: the
                                // first pass proved that nothing at or below it can be in the top-k)
+  int n_splits;                // gridDim.y: the item tiles are cut into this many contiguous ranges,
+  int tiles_per_split;         //   one CTA per (user tile, range); candidates land in per-range
+  int seg;                     //   segments of `seg` = CAND_MAX / n_splits slots: cand_*[(u*S + s)*seg ..]
 };
 
 // One 32-column chunk of one accumulator tile for this thread's user: fast reject by the chunk
@@ -423,6 +426,9 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * TILE_U;
+  const int sp = blockIdx.y;                                   // item range of this CTA
+  const int t_lo = sp * a.tiles_per_split;
+  const int n_t = max(0, min(a.n_tiles, t_lo + a.tiles_per_split) - t_lo);   // tiles of this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -456,11 +462,11 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_BLK_BYTES, &map_a, a_full, kb * KBLK, u0);
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < a.n_tiles; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           mbar_arrive_expect_tx(full + s, B_BLK_BYTES);
-          tma_load_2d(sB + s * B_BLK_BYTES, &map_b, full + s, kb * KBLK, t * TILE_I);
+          tma_load_2d(sB + s * B_BLK_BYTES, &map_b, full + s, kb * KBLK, (t_lo + t) * TILE_I);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
       mbar_wait(a_full, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < a.n_tiles; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         const int buf = t & 1;
         mbar_wait(t_empty + buf, ((t >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -510,14 +516,23 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         const int64_t p0 = a.row_ptr[uid], p1 = a.row_ptr[uid + 1];
         rowp[q] = a.col + p0;
         end[q] = (int)(p1 - p0);
-        if (end[q] > 0) cur[q] = rowp[q][0];
-        if (end[q] > 1) nxt[q] = rowp[q][1];
+        if (t_lo > 0) {  // first rated item inside this CTA's item range
+          int lo = 0, hi = end[q];
+          const int first = t_lo * TILE_I;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rowp[q][mid] < first) lo = mid + 1; else hi = mid;
+          }
+          pos[q] = lo;
+        }
+        if (pos[q] < end[q]) cur[q] = rowp[q][pos[q]];
+        if (pos[q] + 1 < end[q]) nxt[q] = rowp[q][pos[q] + 1];
       }
     }
-    for (int t = 0; t < a.n_tiles; ++t) {
+    for (int t = 0; t < n_t; ++t) {
       const int buf = t & 1;
       mbar_wait(b_empty + buf, ((t >> 1) & 1) ^ 1);
-      const int i0 = t * TILE_I, i1 = i0 + TILE_I;
+      const int i0 = (t_lo + t) * TILE_I, i1 = i0 + TILE_I;
       uint32_t* my = bm + buf * 8 * TILE_U;
       uint32_t w[2][8];
 #pragma unroll
@@ -566,14 +581,14 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int NCH = 8 / EPI;            // chunks per tile for this warp
 
-    for (int t = 0; t < a.n_tiles; ++t) {
+    for (int t = 0; t < n_t; ++t) {
       const int buf = t & 1;
       const uint32_t par = (t >> 1) & 1;
       mbar_wait(t_full + buf, par);
       mbar_wait(b_full + buf, par);
       tc_fence_after();
       const uint32_t* my_bm = bm + buf * 8 * TILE_U + row;
-      const int item0 = t * TILE_I;
+      const int item0 = (t_lo + t) * TILE_I;
       const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I);
       // two chunks in flight: the next tcgen05.ld is issued before the current chunk is scanned
       uint32_t va[32], vb[32];
@@ -615,14 +630,20 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         total += mcnt[x * TILE_U + row];
         tmax = fmaxf(tmax, mthr[x * TILE_U + row]);
       }
-      const int64_t o = (int64_t)(u0 + row) * CAND_MAX + off;
-      for (int x = 0; x < cnt; ++x) {
-        a.cand_id[o + x] = bi[x * TILE_U];
-        a.cand_s[o + x] = bs[x * TILE_U];
+      const int64_t slot = (int64_t)(u0 + row) * a.n_splits + sp;
+      const bool fits = total <= a.seg;
+      if (fits) {
+        const int64_t o = slot * a.seg + off;
+        for (int x = 0; x < cnt; ++x) {
+          a.cand_id[o + x] = bi[x * TILE_U];
+          a.cand_s[o + x] = bs[x * TILE_U];
+        }
       }
       if (hf == 0) {
-        a.cand_cnt[u0 + row] = total;
-        a.cand_thr[u0 + row] = tmax;   // every non-candidate of either half has approx <= its half's thr
+        // every non-candidate of this item range has approx <= the threshold of the buffer that
+        // saw it; a segment that cannot hold the candidates voids the user's proof (thr = +inf)
+        a.cand_cnt[slot] = fits ? total : 0;
+        a.cand_thr[slot] = fits ? tmax : INFINITY;
       }
     }
   }
