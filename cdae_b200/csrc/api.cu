@@ -746,8 +746,21 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
     TRY(ensure(h, h->col_d, (size_t)std::max<int64_t>(nnz, 1)));
   }
   CU(cudaMemcpyAsync(h->row_ptr_d.p, row_ptr, sizeof(int64_t) * (h->U + 1), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->col_d.p, col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
-  h->h2d += sizeof(int64_t) * (h->U + 1) + sizeof(int32_t) * nnz;
+  h->h2d += sizeof(int64_t) * (h->U + 1);
+  if (h->world == 1) {
+    CU(cudaMemcpyAsync(h->col_d.p, col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
+    h->h2d += sizeof(int32_t) * nnz;
+  } else {
+    // a rank only ever reads the rows of the users it trains: upload those slices (one contiguous
+    // range of `col` per minibatch) instead of the whole set on every rank
+    if (!h->plan_valid) TRY(build_plan(h));
+    for (const MiniBatch& p : h->plan) {
+      if (p.n_users == 0) continue;
+      const int64_t s0 = row_ptr[p.uid0], s1 = row_ptr[p.uid0 + p.n_users];
+      if (s1 > s0) CU(cudaMemcpyAsync(h->col_d.p + s0, col + s0, sizeof(int32_t) * (s1 - s0), cudaMemcpyHostToDevice, h->stream));
+      h->h2d += sizeof(int32_t) * (s1 - s0);
+    }
+  }
   return train_epoch_impl(h, seed, epoch, stats);
 }
 

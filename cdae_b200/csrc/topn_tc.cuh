@@ -40,10 +40,13 @@ constexpr int CAND_MAX = 96;  // largest per-user candidate buffer
 // Epilogue warps per TMEM lane quadrant: two while shared memory leaves room for two candidate
 // buffers per user (each warp of a pair takes every other 32-column chunk and keeps its own
 // buffer and threshold), one for the widest operands.
-__host__ __device__ constexpr int epi_warps(int kb) { return kb <= 3 ? 2 : 1; }
+#ifndef TC_KB4_EPI
+#define TC_KB4_EPI 1   // A/B switch (CDAE_NVCC_FLAGS=-DTC_KB4_EPI=2): paired epilogue warps for 4 k-blocks too
+#endif
+__host__ __device__ constexpr int epi_warps(int kb) { return kb <= 3 ? 2 : (kb == 4 ? TC_KB4_EPI : 1); }
 // candidate slots per user (all buffers together): what is left of the 227 KB after A and B
 __host__ __device__ constexpr int cand_slots(int kb) {
-  return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? 48 : 36;
+  return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? (TC_KB4_EPI == 2 ? 54 : 48) : 36;
 }
 __host__ __device__ constexpr int buf_slots(int kb) { return cand_slots(kb) / epi_warps(kb); }
 // a compaction keeps between keep_lo and keep_hi entries of a buffer
@@ -53,7 +56,7 @@ __host__ __device__ constexpr int n_threads(int kb) { return 128 + 128 * epi_war
 constexpr int BM_BYTES = 2 * 8 * TILE_U * 4;  // two rated bitmaps [8 words][128 rows]
 __host__ __device__ constexpr size_t smem_bytes(int kb) {
   return 1024 /*alignment slack*/ + (size_t)kb * A_BLK_BYTES + (size_t)NSTAGE * B_BLK_BYTES +
-         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + 2 * TILE_U * 8 /*merge*/ + 256 /*barriers*/;
+         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + 2 * TILE_U * 8 /*merge*/ + 512 /*exchange, barriers*/;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -368,9 +371,18 @@ struct TcArgs {
 // One 32-column chunk of one accumulator tile for this thread's user: fast reject by the chunk
 // maximum, else scan the 8-column groups that hold a score above thr.  Warp-uniform control flow
 // (votes), so a compaction can run for the whole warp between groups.
+// One 32-column chunk of one accumulator tile for this thread's user: fast reject by the chunk
+// maximum, else look at the 8-column groups that hold a score above thr.  Warp-uniform control flow
+// (votes), so a compaction can run for the whole warp between groups.
+//
+// A group with a hit is almost always hit by ONE lane (one user), so predicating an 8-column scan
+// over the whole warp wastes 31/32 of the work: the sparse path instead lets the hit lane publish
+// its 8 scores through `xch` (32 bytes of shared memory per warp) and lanes 0-7 test one column each
+// and append, cooperatively, to THAT user's buffer.  Dense groups (start of a sweep) keep the
+// predicated scan.
 template <int C2, int KEEP_LO, int KEEP_HI>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t rated, int item_base, float* bs,
-                                           int* bi, int& cnt, float& thr) {
+                                           int* bi, int& cnt, float& thr, float* xch, int lane) {
   float gm[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -382,15 +394,43 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t rat
   if (!__any_sync(0xffffffffu, m > thr)) return;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    if (!__any_sync(0xffffffffu, gm[g] > thr)) continue;
+    unsigned hm = __ballot_sync(0xffffffffu, gm[g] > thr);
+    if (hm == 0) continue;
     // invariant here: cnt <= C2 - 8
+    if (__popc(hm) > 2) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s = __uint_as_float(v[g * 8 + j]);
-      if (s > thr && !((rated >> (g * 8 + j)) & 1u)) {
-        bs[cnt * TILE_U] = s;
-        bi[cnt * TILE_U] = item_base + g * 8 + j;
-        ++cnt;
+      for (int j = 0; j < 8; ++j) {
+        const float s = __uint_as_float(v[g * 8 + j]);
+        if (s > thr && !((rated >> (g * 8 + j)) & 1u)) {
+          bs[cnt * TILE_U] = s;
+          bi[cnt * TILE_U] = item_base + g * 8 + j;
+          ++cnt;
+        }
+      }
+    } else {
+      while (hm) {
+        const int L = __ffs(hm) - 1;
+        hm &= hm - 1;
+        if (lane == L) {
+          *reinterpret_cast<uint4*>(xch) = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+          *reinterpret_cast<uint4*>(xch + 4) = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+        }
+        const float thrL = __shfl_sync(0xffffffffu, thr, L);
+        const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+        const uint32_t ratedL = __shfl_sync(0xffffffffu, rated, L);
+        __syncwarp();
+        const int j = lane & 7;
+        const float s = xch[j];
+        const bool ok = lane < 8 && s > thrL && !((ratedL >> (g * 8 + j)) & 1u);
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int slot = cntL + __popc(okm & ((1u << j) - 1u));
+          // bs / bi point at this lane's own row: lane L's row is (L - lane) floats away
+          bs[slot * TILE_U + (L - lane)] = s;
+          bi[slot * TILE_U + (L - lane)] = item_base + g * 8 + j;
+        }
+        if (lane == L) cnt += __popc(okm);
+        __syncwarp();   // xch is reused by the next hit lane
       }
     }
     if (__any_sync(0xffffffffu, cnt > C2 - 8)) compact<C2, KEEP_LO, KEEP_HI>(bs, bi, &cnt, &thr);
@@ -414,7 +454,8 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
   int* mcnt = reinterpret_cast<int*>(bm + 2 * 8 * TILE_U);          // [2][128] final counts per buffer
   float* mthr = reinterpret_cast<float*>(mcnt + 2 * TILE_U);        // [2][128] final thresholds
   volatile int* creq = reinterpret_cast<volatile int*>(mthr + 2 * TILE_U);  // [2] tile that asked for a compaction
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mthr + 2 * TILE_U + 2);
+  float* xch_all = mthr + 2 * TILE_U + 4;                            // [8 epilogue warps][8] hit exchange (16-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_all + 8 * 8);
   uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA -> TMA
   uint64_t* a_full = bars + 2 * NSTAGE;  // A tile landed
@@ -576,6 +617,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
     const int row = q * 32 + lane;
     float* bs = cs + hf * C2 * TILE_U + row;   // entry e at bs[e * 128]
     int* bi = ci + hf * C2 * TILE_U + row;
+    float* xch = xch_all + e * 8;
     float thr = (a.init_thr && u0 + row < a.n_users) ? a.init_thr[u0 + row] : -INFINITY;
     int cnt = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -598,10 +640,10 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         const int c0 = hf + i * EPI, c1 = hf + (i + 1) * EPI;
         tmem_ld_wait(va);
         tmem_ld32_issue(col0 + (uint32_t)(c1 * 32), vb);
-        scan_chunk<C2, KEEP_LO, KEEP_HI>(va, my_bm[c0 * TILE_U], item0 + c0 * 32, bs, bi, cnt, thr);
+        scan_chunk<C2, KEEP_LO, KEEP_HI>(va, my_bm[c0 * TILE_U], item0 + c0 * 32, bs, bi, cnt, thr, xch, lane);
         tmem_ld_wait(vb);
         if (i + 2 < NCH) tmem_ld32_issue(col0 + (uint32_t)((c1 + EPI) * 32), va);
-        scan_chunk<C2, KEEP_LO, KEEP_HI>(vb, my_bm[c1 * TILE_U], item0 + c1 * 32, bs, bi, cnt, thr);
+        scan_chunk<C2, KEEP_LO, KEEP_HI>(vb, my_bm[c1 * TILE_U], item0 + c1 * 32, bs, bi, cnt, thr, xch, lane);
       }
       tc_fence_before();
       __syncwarp();

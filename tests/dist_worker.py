@@ -67,11 +67,13 @@ def _run(rank, world, local, failures):
         m.dist_init(rank, world, uid[0])
         m.set_params(p)
         steps = 0
-        for epoch in range(2):
-            st = m.train_one_iteration(seed=123, epoch=epoch)
+        for epoch in range(3):
+            # the third epoch takes the training set from host memory (cdae_train_epoch_csr): a rank
+            # uploads only the rows of the users it trains
+            st = m.train_one_iteration(seed=123, epoch=epoch, csr=(rp, col) if epoch == 2 else None)
             steps += st.user_steps
         mine = owned_users(U, B, rank, world)
-        if steps != 2 * len(mine):
+        if steps != 3 * len(mine):
             failures.append("rank %d trained %d user steps, owns %d users" % (rank, steps, len(mine)))
         got = {k: m.get_param(k) for k in ("W", "V", "Wu", "b", "b_prime", "W_ag", "Wu_ag", "b_ag")}
         loss = m.data_loss(seed=7)
@@ -79,7 +81,7 @@ def _run(rank, world, local, failures):
         if rank == 0:
             o = orc.Oracle(cfg, U, I, rp, col)
             o.set_params(p)
-            for epoch in range(2):
+            for epoch in range(3):
                 o.train_epoch(123, epoch, batch_users=B)
             for k, v in got.items():
                 ref = o.param(k)
