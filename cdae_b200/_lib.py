@@ -27,7 +27,8 @@ class Config(C.Structure):
                 ("num_corruptions", C.c_int32), ("using_adagrad", C.c_int32),
                 ("asymmetric", C.c_int32), ("user_factor", C.c_int32), ("linear", C.c_int32),
                 ("scaled", C.c_int32), ("linear_function", C.c_int32), ("tanh_act", C.c_int32),
-                ("batch_users", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("batch_users", C.c_int32), ("device", C.c_int32), ("full_decode", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
 
 
 class EpochStats(C.Structure):
@@ -76,7 +77,8 @@ SIGNATURES = {
 }
 
 KERNEL_CLASSES = ["sample", "gather", "activate", "decode", "hidden_bwd", "scatter", "allreduce",
-                  "apply", "topn", "topn_pack", "topn_rerank", "topn_exact"]
+                  "apply", "topn", "topn_pack", "topn_rerank", "topn_exact",
+                  "fd_pack", "fd_score", "fd_hidden", "fd_itemgrad"]
 
 _lib = None
 

@@ -16,6 +16,7 @@
 #include "handle.cuh"
 #include "topn_kernels.cuh"
 #include "topn_tc.cuh"
+#include "fulldec_tc.cuh"
 #include "train_kernels.cuh"
 
 using namespace cdae;
@@ -386,20 +387,37 @@ static SampleArgs make_sample_args(cdae_handle* h, uint64_t seed, uint32_t pass)
   return sa;
 }
 
+static int run_fulldec(cdae_handle* h, const BatchDev& bt);   // fulldec_api.inl
+
 // gather -> activate -> decode -> hidden_backward -> scatter -> [all-reduce] -> apply
 static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleArgs* sa) {
   const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
   CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per * (h->m.linear_function ? 3 : 2), h->stream));
   TRY(launch_gather(h, bt, sa, true));
   TRY(launch_activate(h, bt, h->m.scale));
-  TRY(launch_decode(h, bt, true, sa));
+  if (h->cfg.full_decode) {
+    TRY(run_fulldec(h, bt));
+  } else {
+    TRY(launch_decode(h, bt, true, sa));
+  }
   if (bt.n_users > 0) {
     ProfScope ps(h, CDAE_K_HIDDEN_BWD);
     const int bx = h->ld / 4, by = std::max(1, 256 / bx);
     hidden_backward_kernel<<<cdiv(bt.n_users, by), dim3(bx, by), sizeof(float4) * bx * by, h->stream>>>(h->m, bt, h->stats_d);
     KERNEL_OK(h);
   }
-  TRY(launch_scatter(h, bt));
+  if (h->cfg.full_decode && !h->m.asym) {
+    // tied weights: every item is an output of every user, so fd_gemm_kernel<.., true> already added
+    // n*lambda*W[i]; an input item's occurrence merges into that one (cdae.hpp:249-250,342-343)
+    // and the scatter must not add a second lambda term
+    ModelDev keep_m = h->m;
+    h->m.lambda = 0.f;
+    const int rc = launch_scatter(h, bt);
+    h->m = keep_m;
+    TRY(rc);
+  } else {
+    TRY(launch_scatter(h, bt));
+  }
   if (h->m.linear_function && bt.n_users > 0) {
     uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt);
     KERNEL_OK(h);
@@ -492,6 +510,12 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
     return set_error(CDAE_E_INVALID, "0 <= num_neg <= %d and num_corruptions >= 1 required", DECODE_MAX_NEGS);
   if (cfg->loss_type < 0 || cfg->loss_type > CDAE_LOSS_LOGM) return set_error(CDAE_E_INVALID, "unknown loss_type %d", cfg->loss_type);
   if (row_ptr[U] >= 0x7fffffff) return set_error(CDAE_E_INVALID, "nnz must be < 2^31");
+  if (cfg->full_decode) {
+    if (cfg->loss_type != CDAE_LOSS_CROSS_ENTROPY && cfg->loss_type != CDAE_LOSS_SQUARE)
+      return set_error(CDAE_E_INVALID, "full_decode needs CROSS_ENTROPY or SQUARE loss");
+    if (cfg->num_dim + 2 > fd::MAX_KB * tc::KBLK)
+      return set_error(CDAE_E_INVALID, "full_decode needs num_dim <= %d", fd::MAX_KB * tc::KBLK - 2);
+  }
   TRY(validate_csr(U, I, row_ptr, col));
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -511,6 +535,8 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, cfg->device));
   h->sm_count = prop.multiProcessorCount;
+  // full decode: one 128-user tile per SM makes every tensor kernel exactly one wave
+  if (cfg->full_decode && cfg->batch_users <= 0) h->batch_users = (int64_t)128 * h->sm_count;
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
@@ -594,6 +620,7 @@ int cdae_destroy(cdae_handle* h) {
   h->test_rp_d.release(); h->test_col_d.release();
   h->tc_zb.release(); h->tc_wb.release(); h->tc_wmax.release(); h->tc_eps.release();
   h->tc_thr.release(); h->tc_redo.release(); h->tc_redo_thr.release();
+  h->fd_zb.release(); h->fd_wb.release(); h->fd_g.release(); h->fd_bits.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -794,7 +821,8 @@ int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8
   int64_t slots = 0, n_in = 0, n_out = 0;
   TRY(stage_users(h, uids, n, true, &slots, &n_in, &n_out));
   if (slots > 0 && !keep_mask) return set_error(CDAE_E_INVALID, "keep_mask is NULL");
-  if (slots * h->cfg.num_neg > 0 && !negatives) return set_error(CDAE_E_INVALID, "negatives is NULL");
+  if (h->cfg.full_decode) negatives = nullptr;   // the output set is every item
+  if (slots * h->cfg.num_neg > 0 && !negatives && !h->cfg.full_decode) return set_error(CDAE_E_INVALID, "negatives is NULL");
   {  // distinct users, non-empty rows, negatives outside the user's row
     std::vector<int64_t> s(uids, uids + n);
     std::sort(s.begin(), s.end());
@@ -803,7 +831,7 @@ int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8
     for (int64_t i = 0; i < n; ++i) {
       const int64_t nu_ = h->row_ptr_h[uids[i] + 1] - h->row_ptr_h[uids[i]];
       if (nu_ == 0) return set_error(CDAE_E_INVALID, "user %lld has no train item (reference CHECK, cdae.hpp:139)", (long long)uids[i]);
-      for (int64_t j = 0; j < nu_ * h->cfg.num_neg; ++j)
+      for (int64_t j = 0; negatives && j < nu_ * h->cfg.num_neg; ++j)
         if (negatives[off * h->cfg.num_neg + j] < 0 || negatives[off * h->cfg.num_neg + j] >= h->I)
           return set_error(CDAE_E_INVALID, "negative id out of range");
       off += nu_;
@@ -811,7 +839,7 @@ int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8
   }
   TRY(ensure_scratch(h, n, slots));
   CU(cudaMemcpyAsync(h->keep.p, keep_mask, (size_t)slots, cudaMemcpyHostToDevice, h->stream));
-  if (slots * h->cfg.num_neg > 0)
+  if (slots * h->cfg.num_neg > 0 && negatives)
     CU(cudaMemcpyAsync(h->negs.p, negatives, sizeof(int32_t) * (size_t)(slots * h->cfg.num_neg), cudaMemcpyHostToDevice, h->stream));
   h->h2d += (size_t)slots + sizeof(int32_t) * (size_t)(slots * h->cfg.num_neg);
   BatchDev bt = make_batch(h, h->tmp_in.p, n_in, h->tmp_out.p, n_out, h->tmp_uids.p, n);
@@ -977,3 +1005,4 @@ static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users
 }
 
 #include "topn_api.inl"
+#include "fulldec_api.inl"

@@ -1,0 +1,143 @@
+// cdae_b200/csrc/fulldec_api.inl — host side of full-item-decode training (fulldec_tc.cuh),
+// included at the end of api.cu.  One frozen minibatch:
+//   pack (W' + b' -> Wb, Z -> Zb)  ->  fd_score (G)  ->  fd_gemm<hidden> (HG)  ->  fd_gemm<itemgrad> (gW', gb')
+// in place of decode_kernel; everything before (gather, activate) and after (hidden_backward,
+// scatter, all-reduce, apply) is the sampled path's.
+
+// The widest split of `units` pieces of work over CTAs of `tiles` output tiles that still fills
+// whole waves of the device: maximise tiles*S / (ceil(tiles*S / SMs) * SMs), S <= max_s.
+static int fd_pick_split(int tiles, int units, int min_units, int sms, int max_s) {
+  double eff[64];
+  double best_eff = 0.;
+  int n = 0;
+  for (int s = 1; s <= max_s && s < 64; ++s) {
+    if (s > 1 && units / s < min_units) break;
+    const int ctas = tiles * s;
+    eff[s] = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+    best_eff = std::max(best_eff, eff[s]);
+    n = s;
+  }
+  // every extra split re-reads one operand and adds a pass of output reductions: take the
+  // smallest split that is within 8% of the best wave efficiency
+  for (int s = 1; s <= n; ++s)
+    if (eff[s] >= 0.92 * best_eff) return s;
+  return 1;
+}
+
+template <int KB, int LT>
+static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const fd::ScoreArgs& a, dim3 grid) {
+  static bool attr_set = false;
+  const size_t dyn = fd::score_smem(KB);
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  fd::fd_score_kernel<KB, LT><<<grid, 384, dyn, h->stream>>>(ma, mb, a);
+  return 0;
+}
+template <int KB, bool ITEMGRAD>
+static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const fd::GemmArgs& a, dim3 grid) {
+  static bool attr_set = false;
+  const size_t dyn = fd::gemm_smem(KB);
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  fd::fd_gemm_kernel<KB, ITEMGRAD><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
+  return 0;
+}
+#define FD_DISPATCH_KB(KBV, CALL)      \
+  switch (KBV) {                       \
+    case 1: TRY(CALL(1)); break;       \
+    case 2: TRY(CALL(2)); break;       \
+    case 3: TRY(CALL(3)); break;       \
+    default: TRY(CALL(4)); break;      \
+  }
+
+// H5-H7 with the output set = all items: fills bt.HG and adds the decoder-side
+// gradients of this rank's users to gW' / gb'.  bt.Z must hold the hidden activations.
+static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
+  if (bt.n_users == 0) return 0;
+  const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
+  const int64_t B_pad = round_up(bt.n_users, 128), I_pad = round_up(h->I, tc::TILE_I);
+  TRY(ensure(h, h->fd_zb, (size_t)(B_pad * Kp)));
+  TRY(ensure(h, h->fd_wb, (size_t)(I_pad * Kp)));
+  TRY(ensure(h, h->fd_g, (size_t)(B_pad * I_pad)));
+  const int64_t words = I_pad / 32;
+  TRY(ensure(h, h->fd_bits, (size_t)(B_pad * words)));
+  const float* Wd = h->m.asym ? h->m.V : h->m.W;
+  float* gWd = h->m.asym ? h->m.gV : h->m.gW;
+  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(h->fd_zb.p);
+  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(h->fd_wb.p);
+  __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(h->fd_g.p);
+  {
+    ProfScope ps(h, CDAE_K_FD_PACK);
+    tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, wb);
+    KERNEL_OK(h);
+    CU(cudaMemsetAsync(h->fd_bits.p, 0, sizeof(uint32_t) * (size_t)(B_pad * words), h->stream));
+    fd::fd_bitmap_kernel<<<cdiv((int64_t)bt.n_users * 32, 256), 256, 0, h->stream>>>(bt.uids, bt.n_users, bt.row_ptr, bt.col, words, h->fd_bits.p);
+    KERNEL_OK(h);
+    fd::pack_z_train_kernel<<<cdiv(B_pad * (Kp / 8), 256), 256, 0, h->stream>>>(bt.Z, bt.n_users, B_pad, K, h->ld, Kp, zb);
+    KERNEL_OK(h);
+  }
+  alignas(64) CUtensorMap m_zb_a, m_wb_b, m_g_rows, m_g_cols, m_wb_mn, m_zb_mn;
+  TRY(tc_make_map(&m_zb_a, zb, (uint64_t)B_pad, (uint64_t)Kp, tc::TILE_U));    // score: A = Zb, 128-user boxes
+  TRY(tc_make_map(&m_wb_b, wb, (uint64_t)I_pad, (uint64_t)Kp, tc::TILE_I));    // score: B = Wb, 256-item boxes
+  TRY(tc_make_map(&m_g_rows, G, (uint64_t)B_pad, (uint64_t)I_pad, 128));       // hidden: A = G, {64 items, 128 users}
+  TRY(tc_make_map(&m_g_cols, G, (uint64_t)B_pad, (uint64_t)I_pad, 64));        // itemgrad: A = G^T, {64 items, 64 users}
+  TRY(tc_make_map(&m_wb_mn, wb, (uint64_t)I_pad, (uint64_t)Kp, 64));           // hidden: B = Wb, {64 cols, 64 items}
+  TRY(tc_make_map(&m_zb_mn, zb, (uint64_t)B_pad, (uint64_t)Kp, 64));           // itemgrad: B = Zb, {64 cols, 64 users}
+  const int u_tiles = (int)(B_pad / 128);
+  {
+    fd::ScoreArgs a;
+    a.n_users = bt.n_users; a.I = h->I; a.I_pad = I_pad; a.n_tiles = (int)(I_pad / tc::TILE_I);
+    a.ksteps = (K + 2 + 15) / 16;
+    a.bits = h->fd_bits.p; a.G = G;
+    a.outputs = &h->stats_d->outputs[0];
+    const int S = fd_pick_split(u_tiles, a.n_tiles, 4, h->sm_count, 32);
+    a.tiles_per_split = (a.n_tiles + S - 1) / S;
+    const dim3 grid(u_tiles, (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    ProfScope ps(h, CDAE_K_FD_SCORE);
+    if (h->m.loss == LOSS_CE) {
+#define CALL(KBV) fd_launch_score<KBV, LOSS_CE>(h, m_zb_a, m_wb_b, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    } else {
+#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_b, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    }
+    KERNEL_OK(h);
+  }
+  {
+    fd::GemmArgs a{};
+    a.n_steps = (int)(I_pad / 64);
+    const int S = fd_pick_split(u_tiles, a.n_steps, 8, h->sm_count, 16);
+    a.steps_per_split = (a.n_steps + S - 1) / S;
+    a.n_rows = bt.n_users; a.K = K; a.ld = h->ld;
+    a.out = bt.HG; a.out_bias = nullptr; a.W = nullptr; a.bp = nullptr; a.nlambda = 0.f;
+    const dim3 grid(u_tiles, (a.n_steps + a.steps_per_split - 1) / a.steps_per_split);
+    ProfScope ps(h, CDAE_K_FD_HIDDEN);
+#define CALL(KBV) fd_launch_gemm<KBV, false>(h, m_g_rows, m_wb_mn, a, grid)
+    FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    KERNEL_OK(h);
+  }
+  {
+    fd::GemmArgs a{};
+    a.n_steps = (int)(B_pad / 64);
+    const int i_tiles = (int)(I_pad / 128);
+    const int S = fd_pick_split(i_tiles, a.n_steps, 8, h->sm_count, 16);
+    a.steps_per_split = (a.n_steps + S - 1) / S;
+    a.n_rows = (int)h->I; a.K = K; a.ld = h->ld;
+    a.out = gWd; a.out_bias = h->m.gbp; a.W = Wd; a.bp = h->m.bp;
+    a.nlambda = (float)bt.n_users * h->m.lambda;
+    const dim3 grid(i_tiles, (a.n_steps + a.steps_per_split - 1) / a.steps_per_split);
+    ProfScope ps(h, CDAE_K_FD_ITEMGRAD);
+#define CALL(KBV) fd_launch_gemm<KBV, true>(h, m_g_cols, m_zb_mn, a, grid)
+    FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    KERNEL_OK(h);
+  }
+  return 0;
+}

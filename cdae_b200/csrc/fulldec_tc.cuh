@@ -1,0 +1,493 @@
+// cdae_b200/csrc/fulldec_tc.cuh — full-item-decode TRAINING on the
+// 5th-generation tensor cores.  The reference scores positives + sampled negatives
+// (cdae.hpp:225-293); with the output set = ALL items the same per-output arithmetic
+//     y = W'[i].z_u + b'[i]      g = l'(y, t_ui)      hg_u += g W'[i]      gW'[i] += g z_u
+// is three dense contractions over a minibatch of B users (6*B*I*K flops):
+//     S  = Z  W'^T   (B x I)     G = l'(S + b', T)            fd_score_kernel
+//     HG = G  W'     (B x K)                                   fd_gemm_kernel<KB, false>
+//     gW'= G^T Z     (I x K)   gb' = G^T 1                     fd_gemm_kernel<KB, true>
+// Operands are bf16 (fp32 accumulation in TMEM), laid out as for the recommend path
+// (topn_tc.cuh): Zb [B_pad][Kp], Wb [I_pad][Kp], Kp = round_up(K+2, 64), column K / K+1 of Zb
+// hold 1 and of Wb the bf16 hi / lo halves of b' — so the bias rides in the first contraction
+// and column K of the third one IS the output-bias gradient.  G is kept in bf16 [B_pad][I_pad]
+// and is written once and read twice; each kernel overlaps that HBM stream with its MMAs.
+//
+// MN-major operands.  The second and third contraction read G and the packed tables ACROSS their
+// storage order (the contraction index is the slow one in memory), which tcgen05 supports for
+// 16-bit types through MN-major shared-memory descriptors: a TMA box of {64 elements (128 bytes) x
+// 64 rows}, 128-byte swizzled, is a [kdim = 64][MN = 64] slab; the descriptor's stride byte offset
+// (1024) steps over groups of eight kdim rows and its leading byte offset (8192 = one box) over
+// 64-wide MN blocks (cute::UMMA canonical layout "((8,n),(8,k)):((1,LBO),(8,SBO))" in 16-byte units).
+#pragma once
+#include "topn_tc.cuh"
+
+namespace cdae {
+namespace fd {
+
+using namespace tc;   // PTX wrappers, TILE_U = 128, TILE_I = 256, KBLK = 64
+
+constexpr int SC_STAGE = 3;                           // score kernel: W' k-blocks in flight
+constexpr int GM_STAGE = 4;                           // gemm kernels: contraction steps in flight
+constexpr int GM_A_BYTES = 128 * KBLK * 2;            // 16 KB: 128 (M) x 64 (kdim), either major
+constexpr int GM_BOX_BYTES = 64 * KBLK * 2;           // 8 KB : one {64, 64} box
+constexpr int MAX_KB = 4;                             // K + 2 <= 256
+
+__host__ __device__ constexpr size_t score_smem(int kb) {
+  return 1024 + (size_t)kb * A_BLK_BYTES + (size_t)SC_STAGE * B_BLK_BYTES + 256;
+}
+__host__ __device__ constexpr size_t gemm_smem(int kb) {
+  return 1024 + (size_t)GM_STAGE * (GM_A_BYTES + (size_t)kb * GM_BOX_BYTES) + 256;
+}
+__host__ __device__ constexpr int tmem_cols(int kb) { return kb == 1 ? 64 : kb == 2 ? 128 : 256; }
+
+// MN-major operand descriptor, SWIZZLE_128B: see the header comment.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_major(int M, int N, int a_mn, int b_mn) {
+  return umma_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+
+// ---------------------------------------------------------------------------------------
+// Zb[r][0..K) = bf16(Z[r]), Zb[r][K] = Zb[r][K+1] = 1, rest 0; rows >= n are 0.  Z is the
+// minibatch-local hidden matrix [n][ld].  One thread per 8 columns.
+__global__ void __launch_bounds__(256) pack_z_train_kernel(const float* __restrict__ Z, int n, int64_t n_pad, int K,
+                                                           int ld, int Kp, __nv_bfloat16* __restrict__ out) {
+  const int g8 = Kp / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * g8) return;
+  const int64_t r = idx / g8;
+  const int c0 = (int)(idx % g8) * 8;
+  __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float v = 0.f;
+    if (r < n) v = c < K ? Z[r * ld + c] : (c <= K + 1 ? 1.f : 0.f);
+    o[j] = __float2bfloat16_rn(v);
+  }
+  *reinterpret_cast<uint4*>(out + r * Kp + c0) = *reinterpret_cast<const uint4*>(o);
+}
+
+// Target bitmap of a minibatch slice: bit i of row r <=> item i is in the train row of user uids[r]
+// (t = 1, cdae.hpp:225-228).  bits [n_pad][words] must be zero; one warp per user.
+__global__ void __launch_bounds__(256) fd_bitmap_kernel(const int32_t* __restrict__ uids, int n,
+                                                        const int64_t* __restrict__ row_ptr,
+                                                        const int32_t* __restrict__ col, int64_t words,
+                                                        uint32_t* __restrict__ bits) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const int64_t uid = uids[r];
+  const int64_t p0 = row_ptr[uid], p1 = row_ptr[uid + 1];
+  uint32_t* row = bits + (int64_t)r * words;
+  for (int64_t p = p0 + lane; p < p1; p += 32) {
+    const int it = __ldg(col + p);
+    atomicOr(row + (it >> 5), 1u << (it & 31));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sigma(y) for two scores at once on the FMA pipe: a = e^-|y| (one MUFU.EX2 each), then
+// 1/(1+a) on [0,1] as a degree-7 polynomial (Chebyshev fit, |rel err| < 1.8e-6 evaluated in fp32)
+// with packed fp32x2 FMAs; sigma(-|y|) = a/(1+a), sigma(|y|) = 1 - sigma(-|y|).  A reciprocal on
+// the SFU would make the kernel MUFU-bound (2 MUFU per score at 16/clk/SM against 0.05 clk of
+// tensor time per score at K = 200).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void sigmoid2(float y0, float y1, float& s0, float& s1) {
+  const float a0 = ex2_approx(-1.4426950408889634f * fabsf(y0));
+  const float a1 = ex2_approx(-1.4426950408889634f * fabsf(y1));
+  const uint64_t a = pack2(a0, a1);
+  uint64_t p = pack2(-0.0492117665708065f, -0.0492117665708065f);
+  p = fma2(p, a, pack2(0.24605883657932281f, 0.24605883657932281f));
+  p = fma2(p, a, pack2(-0.5659353137016296f, -0.5659353137016296f));
+  p = fma2(p, a, pack2(0.8366000652313232f, 0.8366000652313232f));
+  p = fma2(p, a, pack2(-0.9634741544723511f, -0.9634741544723511f));
+  p = fma2(p, a, pack2(0.9957693815231323f, 0.9957693815231323f));
+  p = fma2(p, a, pack2(-0.99980628490448f, -0.99980628490448f));
+  p = fma2(p, a, pack2(0.9999985098838806f, 0.9999985098838806f));
+  float q0, q1;
+  unpack2(mul2(p, a), q0, q1);          // sigma(-|y|) in (0, 0.5]
+  s0 = y0 >= 0.f ? 1.f - q0 : q0;
+  s1 = y1 >= 0.f ? 1.f - q1 : q1;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+struct ScoreArgs {
+  int n_users;               // valid rows of Zb (this rank's slice of the minibatch)
+  int64_t I, I_pad;          // valid items; leading dimension of G (multiple of 256)
+  int n_tiles;               // I_pad / 256
+  int tiles_per_split;       // gridDim.y CTAs share the item tiles of one user tile
+  int ksteps;                // ceil((K + 2) / 16): MMA k-steps that hold non-zero operands
+  const uint32_t* bits;      // [B_pad][I_pad / 32] target bitmap of the slice (fd_bitmap_kernel)
+  __nv_bfloat16* G;          // [B_pad][I_pad] loss gradients dl/dy, 0 in pad rows / pad columns
+  unsigned long long* outputs;  // stats: scored outputs
+};
+
+// One 32-column chunk: y -> g = l'(y, t) -> bf16 -> 64 bytes of this thread's row of G.
+template <int LT>
+__device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
+                                           __nv_bfloat16* gout) {
+  uint32_t o[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float y0 = __uint_as_float(v[j]), y1 = __uint_as_float(v[j + 1]);
+    // target as a float without a conversion: bit j of pos -> 0x3f800000 (1.0f) or 0
+    const float t0 = __uint_as_float(((pos >> j) & 1u) * 0x3f800000u);
+    const float t1 = __uint_as_float(((pos >> (j + 1)) & 1u) * 0x3f800000u);
+    float g0, g1;
+    if (LT == LOSS_CE) {             // loss.hpp:141-147: sigma(y) - t
+      sigmoid2(y0, y1, g0, g1);
+      g0 -= t0;
+      g1 -= t1;
+    } else {                         // SQUARE, loss.hpp:53-55: -2 (t - y)
+      g0 = 2.f * (y0 - t0);
+      g1 = 2.f * (y1 - t1);
+    }
+    o[j >> 1] = pack_bf16x2(g0, g1);
+  }
+  if (valid != 0xffffffffu) {        // warp-uniform: only the padded tail of the last tile
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (!((valid >> (2 * j)) & 1u)) o[j] &= 0xffff0000u;
+      if (!((valid >> (2 * j + 1)) & 1u)) o[j] &= 0x0000ffffu;
+    }
+  }
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = 0u;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(gout);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+
+// S = Zb Wb^T for 128 users x all items of this CTA's range, tile by tile (128 x 256), fused with
+// the loss gradient: the scores never leave TMEM, G goes to global memory in bf16.
+// warp 0 TMA · warp 1 MMA issue · warp 2 owns TMEM · warps 4-11 epilogue (two per TMEM lane
+// quadrant, alternate 32-column chunks; thread = one user).  The targets come from a bitmap of the
+// slice built beforehand (fd_bitmap_kernel): walking the CSR rows inside this kernel, as the
+// recommend kernel does, serialises one dependent global load per positive and made two helper
+// warps the pace of the whole kernel at config C's 145 items per user (profiles/r01_j_*).
+template <int KB, int LT>
+__global__ void __launch_bounds__(384, 1) fd_score_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                          const __grid_constant__ CUtensorMap map_b, ScoreArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                   // KB x [128][64] bf16, swizzled
+  unsigned char* sB = sA + KB * A_BLK_BYTES;                  // SC_STAGE x [256][64] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SC_STAGE * B_BLK_BYTES);
+  uint64_t* full = bars;                  // [SC_STAGE]
+  uint64_t* empty = bars + SC_STAGE;      // [SC_STAGE]
+  uint64_t* a_full = bars + 2 * SC_STAGE;
+  uint64_t* t_full = a_full + 1;          // [2]
+  uint64_t* t_empty = t_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TILE_U;
+  const int t_lo = blockIdx.y * a.tiles_per_split;
+  const int n_t = max(0, min(a.n_tiles, t_lo + a.tiles_per_split) - t_lo);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SC_STAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(a_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full + b, 1);
+      mbar_init(t_empty + b, 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && a.outputs)
+    atomicAdd(a.outputs, (unsigned long long)a.n_users * (unsigned long long)a.I);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_t > 0) {
+      mbar_arrive_expect_tx(a_full, KB * A_BLK_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_BLK_BYTES, &map_a, a_full, kb * KBLK, u0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_t; ++t) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_arrive_expect_tx(full + s, B_BLK_BYTES);
+          tma_load_2d(sB + s * B_BLK_BYTES, &map_b, full + s, kb * KBLK, (t_lo + t) * TILE_I);
+          if (++s == SC_STAGE) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_t > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_U, TILE_I);
+      mbar_wait(a_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_t; ++t) {
+        const int buf = t & 1;
+        mbar_wait(t_empty + buf, ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)buf * TILE_I;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + kb * A_BLK_BYTES), b0 = smem_u32(sB + s * B_BLK_BYTES);
+          const int nk = min(KBLK / 16, a.ksteps - kb * (KBLK / 16));   // trailing k-steps are all zero
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+          umma_commit(empty + s);
+          if (++s == SC_STAGE) { s = 0; ph ^= 1; }
+        }
+        umma_commit(t_full + buf);
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = e & 3;                    // TMEM lane quadrant (= warp % 4)
+    const int hf = e >> 2;                  // chunks hf, hf + 2, ...
+    const int row = q * 32 + lane;
+    const bool row_ok = u0 + row < a.n_users;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    __nv_bfloat16* grow = a.G + (int64_t)(u0 + row) * a.I_pad;
+    // this row's 256 target bits of a tile are 32 contiguous bytes of the slice's bitmap; the words
+    // of tile t + 1 are fetched while tile t is processed (member hf uses words hf, hf+2, hf+4, hf+6)
+    const uint4* brow = reinterpret_cast<const uint4*>(a.bits + (int64_t)(u0 + row) * (a.I_pad / 32)) + (int64_t)t_lo * 2;
+    uint4 nb0 = make_uint4(0u, 0u, 0u, 0u), nb1 = nb0;
+    if (n_t > 0) { nb0 = __ldg(brow); nb1 = __ldg(brow + 1); }
+    for (int t = 0; t < n_t; ++t) {
+      const int buf = t & 1;
+      const uint32_t par = (t >> 1) & 1;
+      const uint4 cb0 = nb0, cb1 = nb1;
+      if (t + 1 < n_t) { nb0 = __ldg(brow + 2 * (t + 1)); nb1 = __ldg(brow + 2 * (t + 1) + 1); }
+      const uint32_t my_bm[4] = {hf ? cb0.y : cb0.x, hf ? cb0.w : cb0.z, hf ? cb1.y : cb1.x, hf ? cb1.w : cb1.z};
+      mbar_wait(t_full + buf, par);
+      tc_fence_after();
+      const int64_t item0 = (int64_t)(t_lo + t) * TILE_I;
+      const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I);
+      uint32_t va[32], vb[32];
+      tmem_ld32_issue(col0 + (uint32_t)(hf * 32), va);
+#pragma unroll
+      for (int i = 0; i < 4; i += 2) {
+        const int c0 = hf + i * 2, c1 = hf + (i + 1) * 2;
+        tmem_ld_wait(va);
+        tmem_ld32_issue(col0 + (uint32_t)(c1 * 32), vb);
+        {
+          const int64_t first = item0 + c0 * 32;
+          const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+          grad_chunk<LT>(va, my_bm[i], valid, row_ok, grow + first);
+        }
+        tmem_ld_wait(vb);
+        if (i + 2 < 4) tmem_ld32_issue(col0 + (uint32_t)((c1 + 2) * 32), va);
+        {
+          const int64_t first = item0 + c1 * 32;
+          const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+          grad_chunk<LT>(vb, my_bm[i + 1], valid, row_ok, grow + first);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct GemmArgs {
+  int n_steps;          // contraction steps of 64 (items for the hidden gradient, users for the item gradient)
+  int steps_per_split;  // gridDim.y CTAs share the contraction; partial sums meet in 16-byte reductions
+  int n_rows;           // valid output rows: users of the slice / items
+  int K, ld;
+  float* out;           // HG [n_users][ld]  |  gW' [I][ld]      (zero, or holding other contributions)
+  float* out_bias;      // item gradient only: gb' [I]
+  const float* W;       // item gradient only: W' and b' for the lambda terms
+  const float* bp;
+  float nlambda;        // (#users of the slice) * lambda: every user contributes lambda*theta per item
+};
+
+// ITEMGRAD = false:  HG[u][k]  = sum_i G[u][i] Wb[i][k]     A = G   (K-major),  B = Wb (MN-major)
+// ITEMGRAD = true :  gW'[i][k] = sum_u G[u][i] Zb[u][k]     A = G^T (MN-major), B = Zb (MN-major)
+//                    (+ n*lambda*W'[i][k]; column K -> gb'[i] + n*lambda*b'[i])
+// One CTA = one 128-row output tile x all Kp columns (accumulator: Kp TMEM columns), walking its
+// share of the contraction in steps of 64 through a GM_STAGE-deep TMA ring.
+// warp 0 TMA · warp 1 MMA issue · warp 2 TMEM owner · warps 4-7 epilogue (thread = output row).
+template <int KB, bool ITEMGRAD>
+__global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                         const __grid_constant__ CUtensorMap map_b, GemmArgs a) {
+  constexpr int STAGE_BYTES = GM_A_BYTES + KB * GM_BOX_BYTES;
+  constexpr int NCOL = KB * KBLK;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGE * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + GM_STAGE;
+  uint64_t* t_full = bars + 2 * GM_STAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int s_lo = blockIdx.y * a.steps_per_split;
+  const int n_s = max(0, min(a.n_steps, s_lo + a.steps_per_split) - s_lo);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GM_STAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(t_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols(KB));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_s; ++t) {
+        mbar_wait(empty + s, ph ^ 1);
+        unsigned char* st = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(full + s, STAGE_BYTES);
+        const int k0 = (s_lo + t) * KBLK;   // first contraction index of the step
+        if (ITEMGRAD) {
+          // G^T: rows = users k0.., 128 bytes = 64 items; two boxes cover the tile's 128 items
+          tma_load_2d(st, &map_a, full + s, m0, k0);
+          tma_load_2d(st + GM_BOX_BYTES, &map_a, full + s, m0 + 64, k0);
+        } else {
+          // G: rows = the tile's 128 users, 128 bytes = items k0..k0+63
+          tma_load_2d(st, &map_a, full + s, k0, m0);
+        }
+        for (int kb = 0; kb < KB; ++kb)   // rows = contraction index, 128 bytes = columns kb*64..
+          tma_load_2d(st + GM_A_BYTES + kb * GM_BOX_BYTES, &map_b, full + s, kb * KBLK, k0);
+        if (++s == GM_STAGE) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_s > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_major(128, NCOL, ITEMGRAD ? 1 : 0, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_s; ++t) {
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + GM_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KBLK / 16; ++k) {
+          // 16 contraction indices: 32 bytes along a K-major row, 16 rows (2048 bytes) of an MN-major slab
+          const uint64_t ad = ITEMGRAD ? umma_desc_mn_sw128(a0 + k * 2048, GM_BOX_BYTES) : umma_desc_sw128(a0 + k * 32);
+          const uint64_t bd = umma_desc_mn_sw128(b0 + k * 2048, GM_BOX_BYTES);
+          umma_bf16(tmem_base, ad, bd, idesc, (t | k) != 0);
+        }
+        umma_commit(empty + s);
+        if (++s == GM_STAGE) { s = 0; ph ^= 1; }
+      }
+      umma_commit(t_full);
+    }
+  } else if (warp >= 4 && n_s > 0) {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < a.n_rows;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    mbar_wait(t_full, 0);
+    tc_fence_after();
+    const int last_col = ITEMGRAD ? a.K : a.K - 1;     // column K of the item gradient is gb'
+    const bool add_l2 = ITEMGRAD && blockIdx.y == 0 && a.nlambda != 0.f;
+    for (int c = 0; c * 32 <= last_col; ++c) {
+      uint32_t v[32];
+      tmem_ld32_issue(lane_addr + (uint32_t)(c * 32), v);
+      tmem_ld_wait(v);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = c * 32 + j;
+        if (col > last_col) break;
+        float x[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+        if (ITEMGRAD && col <= a.K && col + 3 >= a.K) {
+          const int kk = a.K - col;
+          float gb = kk == 0 ? x[0] : kk == 1 ? x[1] : kk == 2 ? x[2] : x[3];
+          if (add_l2) gb = fmaf(a.nlambda, a.bp[row], gb);
+          red_add_f32(a.out_bias + row, gb);
+        }
+        if (col < a.K) {
+          if (add_l2) {
+            const float4 w = ld4(a.W + (int64_t)row * a.ld + col);   // pad columns of W' are 0
+            x[0] = fmaf(a.nlambda, w.x, x[0]); x[1] = fmaf(a.nlambda, w.y, x[1]);
+            x[2] = fmaf(a.nlambda, w.z, x[2]); x[3] = fmaf(a.nlambda, w.w, x[3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i >= a.K) x[i] = 0.f;                        // bias columns: not part of the row
+          red_add_v4(a.out + (int64_t)row * a.ld + col, make_float4(x[0], x[1], x[2], x[3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols(KB));
+  }
+}
+
+}  // namespace fd
+}  // namespace cdae
+static_assert(cdae::fd::score_smem(4) <= 232448 && cdae::fd::gemm_smem(4) <= 232448,
+              "full-decode kernels exceed the 227 KB of shared memory a CTA can opt into");

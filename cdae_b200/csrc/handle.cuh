@@ -94,6 +94,9 @@ struct cdae_handle {
   int64_t topn_pass2_users = 0;          // users that needed the second tensor sweep
   int64_t topn_tc_users = 0, topn_redo_users = 0;  // last cdae_topn_build: verified on the tensor path / redone exactly
   int topn_path = 0;                     // 0 fp32 CUDA cores, 1 tcgen05
+  // full-item-decode training (fulldec_tc.cuh): bf16 operands and the loss-gradient matrix
+  cdae::DevBuf<uint16_t> fd_zb, fd_wb, fd_g;   // [B_pad][Kp], [I_pad][Kp], [B_pad][I_pad]
+  cdae::DevBuf<uint32_t> fd_bits;              // [B_pad][I_pad / 32] target bitmap of the slice
   cdae::DevBuf<int64_t> test_rp_d;
   cdae::DevBuf<int32_t> test_col_d;
   std::vector<int32_t> topn_ids_h;    // host mirror for thread-safe lookups

@@ -47,6 +47,7 @@ class CDAEConfig:
         self.tanh = bool(c.tanh_act)
         self.batch_users = 0
         self.device = 0
+        self.full_decode = False        # H12: decode against all items on tcgen05 (no reference function)
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise KeyError(k)
@@ -63,6 +64,7 @@ class CDAEConfig:
         c.user_factor, c.linear, c.scaled = int(self.user_factor), int(self.linear), int(self.scaled)
         c.linear_function, c.tanh_act = int(self.linear_function), int(self.tanh)
         c.batch_users, c.device = int(self.batch_users), int(self.device)
+        c.full_decode = int(self.full_decode)
         return c
 
 
@@ -159,10 +161,10 @@ class CDAE:
         """One frozen minibatch of distinct users with explicit masks / negatives."""
         u = _arr(uids, np.int64)
         k = _arr(keep_mask, np.uint8)
-        n = _arr(negatives, np.int32)
+        n = None if negatives is None else _arr(negatives, np.int32)
         st = EpochStats()
         _lib.check(self._L.cdae_train_users(self._h, _ptr(u, _lib.i64p), len(u), _ptr(k, _lib.u8p),
-                                            _ptr(n, _lib.i32p), C.byref(st)))
+                                            None if n is None else _ptr(n, _lib.i32p), C.byref(st)))
         self.last_stats = st
         self._topk = 0
         return st

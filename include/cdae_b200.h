@@ -83,7 +83,13 @@ typedef struct cdae_config {
   int32_t batch_users;        /* users per frozen minibatch; 0 -> 8192.  1 reproduces the
                                  reference's per-user online step. */
   int32_t device;             /* CUDA device ordinal */
-  int32_t reserved[7];
+  int32_t full_decode;        /* 1: full-item decode — every user's output set is ALL items (target 1
+                                 on the train row, 0 elsewhere) instead of positives + num_neg
+                                 sampled negatives; the K x I contraction runs on tcgen05/TMEM with
+                                 bf16 operands (no reference function: SURVEY.md H12).  Needs
+                                 CROSS_ENTROPY or SQUARE loss and num_dim <= 254; batch_users 0 ->
+                                 128 x SM count. */
+  int32_t reserved[6];
 } cdae_config_t;
 
 typedef struct cdae_epoch_stats {
@@ -142,7 +148,8 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
 /* CDAE::train_one_user_corruption (cdae.hpp:198-358) for n DISTINCT users as ONE frozen
  * minibatch with EXPLICIT randomness: keep_mask has one byte per train item of each listed
  * user (CSR order, concatenated); negatives has n_u*num_neg item ids per user, concatenated
- * (each must be outside that user's row).  n = 1 is the reference's online step. */
+ * (each must be outside that user's row; ignored, may be NULL, with full_decode).  n = 1 is the
+ * reference's online step. */
 int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* keep_mask,
                      const int32_t* negatives, cdae_epoch_stats_t* stats);
 
@@ -190,7 +197,9 @@ int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl
 enum cdae_kernel_class {
   CDAE_K_SAMPLE = 0, CDAE_K_GATHER, CDAE_K_ACTIVATE, CDAE_K_DECODE, CDAE_K_HIDDEN_BWD,
   CDAE_K_SCATTER, CDAE_K_ALLREDUCE, CDAE_K_APPLY, CDAE_K_TOPN /* tcgen05 candidate kernel */,
-  CDAE_K_TOPN_PACK, CDAE_K_TOPN_RERANK, CDAE_K_TOPN_EXACT /* fp32 candidate kernel */, CDAE_K_COUNT
+  CDAE_K_TOPN_PACK, CDAE_K_TOPN_RERANK, CDAE_K_TOPN_EXACT /* fp32 candidate kernel */,
+  /* full-item decode training (tcgen05): scores + loss gradient, hidden gradient, item gradient */
+  CDAE_K_FD_PACK, CDAE_K_FD_SCORE, CDAE_K_FD_HIDDEN, CDAE_K_FD_ITEMGRAD, CDAE_K_COUNT
 };
 int cdae_profile(cdae_handle* h, int32_t enable);
 int cdae_profile_get(cdae_handle* h, double* ms_out /*[CDAE_K_COUNT]*/,

@@ -403,9 +403,29 @@ static void touch(int64_t** list, int64_t* n, int64_t* cap, char* flag, int64_t 
 /* ext == NULL: the frozen-batch step.  ext != NULL (data-parallel shard): the item-side
  * gradients are ADDED to ext = [gW (I*K) | gV (I*K, asymmetric only) | gb' (I) | gb (K)] instead
  * of being applied; only the user-private rows (Wu, Uu) are updated here. */
+/* bf16 round-to-nearest-even of a value that first goes through fp32 — the operand format of the
+ * tcgen05 full-item decode (cdae_b200/csrc/fulldec_tc.cuh). */
+static double round_bf16(double x) {
+  float f = (float)x;
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (double)f; /* inf / nan */
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  memcpy(&f, &u, 4);
+  return (double)f;
+}
+static int row_contains(const orc_model* m, int64_t uid, int64_t item);
+
+/* full != 0 (H12, no reference function — SURVEY.md F4): the output set of every user is ALL I
+ * items, target 1 on the user's train row and 0 elsewhere, i.e. the same step with "negatives =
+ * every non-positive once"; negs / neg_ptr are ignored.  rounding != 0 additionally restates the
+ * operand rounding of the tensor-core path: z, W' rows and g are rounded to bf16 where they enter
+ * the three contractions (y = z.W', hg = sum g W', gW' = sum g z), b' enters y as its bf16 hi+lo
+ * pair; products, sums, lambda terms and everything outside the decode stay exact. */
 static void step_frozen_impl(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
                              const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
-                             double* loss_sum_out, double* ext) {
+                             double* loss_sum_out, double* ext, int full, int rounding) {
   const int K = m->K;
   const orc_config* c = &m->cfg;
   const int64_t I = m->I;
@@ -422,10 +442,12 @@ static void step_frozen_impl(orc_model* m, int64_t n_users, const int64_t* uids,
   ws.flagbp = (char*)calloc((size_t)I, 1);
   double* gWu = (double*)calloc((size_t)n_users * (size_t)K, sizeof(double));
   double* gUu = (double*)calloc((size_t)n_users * (size_t)K, sizeof(double));
-  double* z = (double*)malloc(sizeof(double) * (size_t)K * 4);
+  double* z = (double*)malloc(sizeof(double) * (size_t)K * 6);
   double* d = z + K;
   double* hg = d + K;
   double* hd = hg + K;
+  double* zr = hd + K; /* bf16-rounded z (rounding mode) */
+  double* wr = zr + K; /* bf16-rounded W' row */
   double loss_sum = 0.;
 
   const double* Wd = c->asymmetric ? m->p[ORC_V] : m->p[ORC_W];
@@ -435,32 +457,46 @@ static void step_frozen_impl(orc_model* m, int64_t n_users, const int64_t* uids,
     const int64_t uid = uids[ui];
     const int64_t* in = in_items + in_ptr[ui];
     const int64_t n_in = in_ptr[ui + 1] - in_ptr[ui];
-    const int64_t* ng = negs + neg_ptr[ui];
-    const int64_t n_ng = neg_ptr[ui + 1] - neg_ptr[ui];
+    const int64_t* ng = full ? NULL : negs + neg_ptr[ui];
+    const int64_t n_ng = full ? 0 : neg_ptr[ui + 1] - neg_ptr[ui];
     const int64_t n_out = m->row_ptr[uid + 1] - m->row_ptr[uid];
     const int32_t* out = m->col + m->row_ptr[uid];
     orc_hidden(m, uid, in, n_in, scale, z);
     act_deriv(m, z, d);
     for (int k = 0; k < K; ++k) hg[k] = 0.;
-    for (int64_t t = 0; t < n_out + n_ng; ++t) {
-      const int is_pos = t < n_out;
-      const int64_t iid = is_pos ? (int64_t)out[t] : ng[t - n_out];
+    if (rounding)
+      for (int k = 0; k < K; ++k) zr[k] = round_bf16(z[k]);
+    const int64_t n_total = full ? I : n_out + n_ng;
+    for (int64_t t = 0; t < n_total; ++t) {
+      const int is_pos = full ? row_contains(m, uid, t) : t < n_out;
+      const int64_t iid = full ? t : (is_pos ? (int64_t)out[t] : ng[t - n_out]);
       const double truth = is_pos ? 1. : 0.;
-      double y = orc_output(m, z, iid);
+      const double* row = Wd + iid * K;
+      double y;
+      if (rounding) {
+        const double bp = m->p[ORC_BPRIME][iid], bhi = round_bf16(bp);
+        y = 0.;
+        for (int k = 0; k < K; ++k) { wr[k] = round_bf16(row[k]); y += zr[k] * wr[k]; }
+        y += bhi + round_bf16(bp - bhi);
+      } else {
+        y = orc_output(m, z, iid);
+      }
       double gradient = orc_loss_gradient(c->loss_type, y, truth);
       loss_sum += orc_loss_evaluate(c->loss_type, y, truth);
+      if (rounding) gradient = round_bf16(gradient);
       ws.gbp[iid] += gradient + c->lambda * m->p[ORC_BPRIME][iid];
       touch(&ws.touchbp, &ws.nbp, &ws.capbp, ws.flagbp, iid);
-      const double* row = Wd + iid * K;
-      for (int k = 0; k < K; ++k) hg[k] += gradient * row[k];
+      const double* zc = rounding ? zr : z;   /* what enters gW' = sum g z */
+      const double* rc = rounding ? wr : row; /* what enters hg = sum g W' */
+      for (int k = 0; k < K; ++k) hg[k] += gradient * rc[k];
       /* tied & positive & in the corrupted input: the occurrence merges into the input-row
        * update (one lambda term there, cdae.hpp:249-250,342-343); else lambda term here. */
       int merged = is_pos && !c->asymmetric && in_sorted_or_linear(in, n_in, iid);
       double* g = gWd + iid * K;
       if (merged)
-        for (int k = 0; k < K; ++k) g[k] += gradient * z[k];
+        for (int k = 0; k < K; ++k) g[k] += gradient * zc[k];
       else
-        for (int k = 0; k < K; ++k) g[k] += gradient * z[k] + c->lambda * row[k];
+        for (int k = 0; k < K; ++k) g[k] += gradient * zc[k] + c->lambda * row[k];
       if (c->asymmetric)
         touch(&ws.touchV, &ws.nV, &ws.capV, ws.flagV, iid);
       else
@@ -532,13 +568,23 @@ static void step_frozen_impl(orc_model* m, int64_t n_users, const int64_t* uids,
 void orc_step_frozen(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
                      const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
                      double* loss_sum_out) {
-  step_frozen_impl(m, n_users, uids, in_ptr, in_items, neg_ptr, negs, loss_sum_out, NULL);
+  step_frozen_impl(m, n_users, uids, in_ptr, in_items, neg_ptr, negs, loss_sum_out, NULL, 0, 0);
+}
+
+void orc_step_frozen_full(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                          const int64_t* in_items, int rounding, double* loss_sum_out) {
+  step_frozen_impl(m, n_users, uids, in_ptr, in_items, NULL, NULL, loss_sum_out, NULL, 1, rounding);
+}
+void orc_shard_gradients_full(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                              const int64_t* in_items, int rounding, double* loss_sum_out,
+                              double* dense_grad) {
+  step_frozen_impl(m, n_users, uids, in_ptr, in_items, NULL, NULL, loss_sum_out, dense_grad, 1, rounding);
 }
 
 void orc_shard_gradients(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
                          const int64_t* in_items, const int64_t* neg_ptr, const int64_t* negs,
                          double* loss_sum_out, double* dense_grad) {
-  step_frozen_impl(m, n_users, uids, in_ptr, in_items, neg_ptr, negs, loss_sum_out, dense_grad);
+  step_frozen_impl(m, n_users, uids, in_ptr, in_items, neg_ptr, negs, loss_sum_out, dense_grad, 0, 0);
 }
 
 /* One upd per element whose summed gradient is non-zero (upd with g = 0 is a no-op, so this
@@ -856,6 +902,45 @@ double orc_train_epoch(orc_model* m, uint64_t seed, int64_t epoch, int64_t batch
     }
     free(uids); free(in_ptr); free(neg_ptr); free(in); free(negs); free(keep);
   }
+  return loss_total;
+}
+
+/* One epoch of full-item-decode training (H12): frozen minibatches of batch_users consecutive
+ * users, Philox keep masks as in orc_train_epoch, no negatives. */
+double orc_train_epoch_full(orc_model* m, uint64_t seed, int64_t epoch, int64_t batch_users,
+                            int64_t u0, int64_t u1, int rounding) {
+  const int cnum = m->cfg.num_corruptions;
+  double loss_total = 0.;
+  if (batch_users < 1) batch_users = 1;
+  int64_t maxn = 1;
+  for (int64_t u = u0; u < u1; ++u)
+    if (m->row_ptr[u + 1] - m->row_ptr[u] > maxn) maxn = m->row_ptr[u + 1] - m->row_ptr[u];
+  uint8_t* keep = (uint8_t*)malloc((size_t)maxn);
+  for (int64_t b0 = u0; b0 < u1; b0 += batch_users) {
+    const int64_t b1 = b0 + batch_users < u1 ? b0 + batch_users : u1, nb = b1 - b0;
+    const int64_t nnz = m->row_ptr[b1] - m->row_ptr[b0];
+    int64_t* uids = (int64_t*)malloc(sizeof(int64_t) * (size_t)nb);
+    int64_t* in_ptr = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nb + 1));
+    int64_t* in = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
+    for (int cidx = 0; cidx < cnum; ++cidx) {
+      const uint32_t pass = (uint32_t)(epoch * cnum + cidx);
+      in_ptr[0] = 0;
+      for (int64_t i = 0; i < nb; ++i) {
+        const int64_t u = b0 + i, s0 = m->row_ptr[u], n = m->row_ptr[u + 1] - s0;
+        uids[i] = u;
+        orc_sample_keep(m, seed, pass, u, keep);
+        int64_t n_in = 0;
+        for (int64_t s = 0; s < n; ++s)
+          if (keep[s]) in[in_ptr[i] + n_in++] = m->col[s0 + s];
+        in_ptr[i + 1] = in_ptr[i] + n_in;
+      }
+      double ls = 0.;
+      orc_step_frozen_full(m, nb, uids, in_ptr, in, rounding, &ls);
+      loss_total += ls;
+    }
+    free(uids); free(in_ptr); free(in);
+  }
+  free(keep);
   return loss_total;
 }
 

@@ -88,6 +88,21 @@ void orc_shard_gradients(orc_model* m, int64_t n_users, const int64_t* uids,
                          double* dense_grad);
 void orc_apply_dense(orc_model* m, const double* dense_grad, int any_steps);
 
+/* H12, full-item-decode training (an EXTENSION: the reference has no such function):
+ * the frozen-batch step above with every user's output set = all I items (target 1 on the train
+ * row, 0 elsewhere) — identical to orc_step_frozen called with "negatives = every non-positive
+ * item once" (tests/test_oracle_golden.py asserts that).  rounding = 1 additionally restates the
+ * bf16 operand rounding of the tensor-core path (z, W', g to bf16 where they enter the three
+ * contractions; b' as a bf16 hi+lo pair) so that the CUDA kernels can be checked tightly;
+ * rounding = 0 is plain fp64. */
+void orc_step_frozen_full(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                          const int64_t* in_items, int rounding, double* loss_sum_out);
+void orc_shard_gradients_full(orc_model* m, int64_t n_users, const int64_t* uids, const int64_t* in_ptr,
+                              const int64_t* in_items, int rounding, double* loss_sum_out,
+                              double* dense_grad);
+double orc_train_epoch_full(orc_model* m, uint64_t seed, int64_t epoch, int64_t batch_users,
+                            int64_t u0, int64_t u1, int rounding);
+
 /* cdae.hpp:162-196 with rated = the user's train row.  ids sorted by score desc
  * (exact-score ties: lower id first; the reference leaves tie order unspecified). */
 int orc_recommend(const orc_model* m, int64_t uid, int64_t topk, int64_t* ids_out,

@@ -92,6 +92,11 @@ def _orc():
         L.orc_shard_gradients.argtypes = [C.c_void_p, C.c_int64, i64p, i64p, i64p, i64p, i64p, f64p,
                                           f64p]
         L.orc_apply_dense.argtypes = [C.c_void_p, f64p, C.c_int]
+        L.orc_step_frozen_full.argtypes = [C.c_void_p, C.c_int64, i64p, i64p, i64p, C.c_int, f64p]
+        L.orc_shard_gradients_full.argtypes = [C.c_void_p, C.c_int64, i64p, i64p, i64p, C.c_int, f64p, f64p]
+        L.orc_train_epoch_full.restype = C.c_double
+        L.orc_train_epoch_full.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64,
+                                           C.c_int64, C.c_int]
         L.orc_recommend.restype = C.c_int
         L.orc_recommend.argtypes = [C.c_void_p, C.c_int64, C.c_int64, i64p, f64p]
         L.orc_data_loss.restype = C.c_double
@@ -209,6 +214,34 @@ class Oracle:
         self._L.orc_step_frozen(self._h, len(uids), _p(uids, i64p), _p(in_ptr, i64p),
                                 _p(ins, i64p), _p(neg_ptr, i64p), _p(ngs, i64p), C.byref(ls))
         return ls.value
+
+    def step_frozen_full(self, uids, in_lists, rounding=0):
+        """H12: frozen minibatch with every user's output set = all items (no reference
+        function; == step_frozen with negatives = every non-positive once).  rounding=1 restates
+        the bf16 operand rounding of the tensor-core path."""
+        uids = _as(uids, np.int64)
+        in_ptr = np.zeros(len(uids) + 1, np.int64)
+        in_ptr[1:] = np.cumsum([len(x) for x in in_lists])
+        ins = _as(np.concatenate([np.asarray(x, np.int64) for x in in_lists] + [np.zeros(0, np.int64)]), np.int64)
+        ls = C.c_double(0)
+        self._L.orc_step_frozen_full(self._h, len(uids), _p(uids, i64p), _p(in_ptr, i64p), _p(ins, i64p),
+                                     int(rounding), C.byref(ls))
+        return ls.value
+
+    def shard_gradients_full(self, uids, in_lists, dense, rounding=0):
+        uids = _as(uids, np.int64)
+        in_ptr = np.zeros(len(uids) + 1, np.int64)
+        in_ptr[1:] = np.cumsum([len(x) for x in in_lists])
+        ins = _as(np.concatenate([np.asarray(x, np.int64) for x in in_lists] + [np.zeros(0, np.int64)]), np.int64)
+        assert dense.dtype == np.float64 and dense.flags.c_contiguous and dense.size == self.dense_grad_size()
+        ls = C.c_double(0)
+        self._L.orc_shard_gradients_full(self._h, len(uids), _p(uids, i64p), _p(in_ptr, i64p), _p(ins, i64p),
+                                         int(rounding), C.byref(ls), _p(dense, f64p))
+        return ls.value
+
+    def train_epoch_full(self, seed, epoch, batch_users, rounding=0, u0=0, u1=None):
+        u1 = self.U if u1 is None else u1
+        return self._L.orc_train_epoch_full(self._h, seed, epoch, batch_users, u0, u1, int(rounding))
 
     def dense_grad_size(self):
         """[gW | gV (asymmetric) | gb' | gb] — the buffer the GPU path all-reduces."""
