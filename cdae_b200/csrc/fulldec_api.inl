@@ -25,14 +25,15 @@ static int fd_pick_split(int tiles, int units, int min_units, int sms, int max_s
 }
 
 template <int KB, int LT>
-static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const fd::ScoreArgs& a, dim3 grid) {
+static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mg,
+                           const fd::ScoreArgs& a, dim3 grid) {
   static bool attr_set = false;
   const size_t dyn = fd::score_smem(KB);
   if (!attr_set) {
     CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  fd::fd_score_kernel<KB, LT><<<grid, 384, dyn, h->stream>>>(ma, mb, a);
+  fd::fd_score_kernel<KB, LT><<<grid, 640, dyn, h->stream>>>(ma, mb, mg, a);
   return 0;
 }
 template <int KB, bool ITEMGRAD>
@@ -80,7 +81,8 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     fd::pack_z_train_kernel<<<cdiv(B_pad * (Kp / 8), 256), 256, 0, h->stream>>>(bt.Z, bt.n_users, B_pad, K, h->ld, Kp, zb);
     KERNEL_OK(h);
   }
-  alignas(64) CUtensorMap m_zb_a, m_wb_b, m_g_rows, m_g_cols, m_wb_mn, m_zb_mn;
+  alignas(64) CUtensorMap m_zb_a, m_wb_b, m_g_st, m_g_rows, m_g_cols, m_wb_mn, m_zb_mn;
+  TRY(tc_make_map(&m_g_st, G, (uint64_t)B_pad, (uint64_t)I_pad, 32));          // score: G store, {64 items, 32 users}
   TRY(tc_make_map(&m_zb_a, zb, (uint64_t)B_pad, (uint64_t)Kp, tc::TILE_U));    // score: A = Zb, 128-user boxes
   TRY(tc_make_map(&m_wb_b, wb, (uint64_t)I_pad, (uint64_t)Kp, tc::TILE_I));    // score: B = Wb, 256-item boxes
   TRY(tc_make_map(&m_g_rows, G, (uint64_t)B_pad, (uint64_t)I_pad, 128));       // hidden: A = G, {64 items, 128 users}
@@ -99,11 +101,11 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     const dim3 grid(u_tiles, (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
     ProfScope ps(h, CDAE_K_FD_SCORE);
     if (h->m.loss == LOSS_CE) {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_CE>(h, m_zb_a, m_wb_b, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_CE>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     } else {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_b, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     }

@@ -27,13 +27,14 @@ namespace fd {
 using namespace tc;   // PTX wrappers, TILE_U = 128, TILE_I = 256, KBLK = 64
 
 constexpr int SC_STAGE = 3;                           // score kernel: W' k-blocks in flight
+constexpr int SC_STG_BYTES = 32 * 128;                // score kernel: one warp's staging tile
 constexpr int GM_STAGE = 4;                           // gemm kernels: contraction steps in flight
 constexpr int GM_A_BYTES = 128 * KBLK * 2;            // 16 KB: 128 (M) x 64 (kdim), either major
 constexpr int GM_BOX_BYTES = 64 * KBLK * 2;           // 8 KB : one {64, 64} box
 constexpr int MAX_KB = 4;                             // K + 2 <= 256
 
 __host__ __device__ constexpr size_t score_smem(int kb) {
-  return 1024 + (size_t)kb * A_BLK_BYTES + (size_t)SC_STAGE * B_BLK_BYTES + 256;
+  return 1024 + (size_t)kb * A_BLK_BYTES + (size_t)SC_STAGE * B_BLK_BYTES + 16 * SC_STG_BYTES + 256;
 }
 __host__ __device__ constexpr size_t gemm_smem(int kb) {
   return 1024 + (size_t)GM_STAGE * (GM_A_BYTES + (size_t)kb * GM_BOX_BYTES) + 256;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) fd_bitmap_kernel(const int32_t* __restric
 
 // ---------------------------------------------------------------------------------------
 // sigma(y) for two scores at once on the FMA pipe: a = e^-|y| (one MUFU.EX2 each), then
-// 1/(1+a) on [0,1] as a degree-7 polynomial (Chebyshev fit, |rel err| < 1.8e-6 evaluated in fp32)
+// 1/(1+a) on [0,1] as a degree-6 polynomial (Chebyshev fit, |rel err| < 9e-6 evaluated in fp32)
 // with packed fp32x2 FMAs; sigma(-|y|) = a/(1+a), sigma(|y|) = 1 - sigma(-|y|).  A reciprocal on
 // the SFU would make the kernel MUFU-bound (2 MUFU per score at 16/clk/SM against 0.05 clk of
 // tensor time per score at K = 200).
@@ -126,14 +127,13 @@ __device__ __forceinline__ void sigmoid2(float y0, float y1, float& s0, float& s
   const float a0 = ex2_approx(-1.4426950408889634f * fabsf(y0));
   const float a1 = ex2_approx(-1.4426950408889634f * fabsf(y1));
   const uint64_t a = pack2(a0, a1);
-  uint64_t p = pack2(-0.0492117665708065f, -0.0492117665708065f);
-  p = fma2(p, a, pack2(0.24605883657932281f, 0.24605883657932281f));
-  p = fma2(p, a, pack2(-0.5659353137016296f, -0.5659353137016296f));
-  p = fma2(p, a, pack2(0.8366000652313232f, 0.8366000652313232f));
-  p = fma2(p, a, pack2(-0.9634741544723511f, -0.9634741544723511f));
-  p = fma2(p, a, pack2(0.9957693815231323f, 0.9957693815231323f));
-  p = fma2(p, a, pack2(-0.99980628490448f, -0.99980628490448f));
-  p = fma2(p, a, pack2(0.9999985098838806f, 0.9999985098838806f));
+  uint64_t p = pack2(0.07170680165290833f, 0.07170680165290833f);
+  p = fma2(p, a, pack2(-0.32268059253692627f, -0.32268059253692627f));
+  p = fma2(p, a, pack2(0.6677695512771606f, 0.6677695512771606f));
+  p = fma2(p, a, pack2(-0.9030575156211853f, -0.9030575156211853f));
+  p = fma2(p, a, pack2(0.9854083061218262f, 0.9854083061218262f));
+  p = fma2(p, a, pack2(-0.9991334080696106f, -0.9991334080696106f));
+  p = fma2(p, a, pack2(0.999991238117218f, 0.999991238117218f));
   float q0, q1;
   unpack2(mul2(p, a), q0, q1);          // sigma(-|y|) in (0, 0.5]
   s0 = y0 >= 0.f ? 1.f - q0 : q0;
@@ -156,10 +156,12 @@ struct ScoreArgs {
   unsigned long long* outputs;  // stats: scored outputs
 };
 
-// One 32-column chunk: y -> g = l'(y, t) -> bf16 -> 64 bytes of this thread's row of G.
+// One 32-column chunk: y -> g = l'(y, t) -> bf16 -> 64 bytes of this thread's row of the warp's
+// staging tile ([32 rows][128 bytes], 128-byte swizzled like every TMA tile: 16-byte piece c of
+// row r lives at piece c ^ (r & 7)); cbase = 0 / 4 selects the half of the row.
 template <int LT>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
-                                           __nv_bfloat16* gout) {
+                                           unsigned char* srow, int cbase, int sw) {
   uint32_t o[16];
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
@@ -189,26 +191,40 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = 0u;
   }
-  uint4* dst = reinterpret_cast<uint4*>(gout);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(srow + (((cbase + j) ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // S = Zb Wb^T for 128 users x all items of this CTA's range, tile by tile (128 x 256), fused with
 // the loss gradient: the scores never leave TMEM, G goes to global memory in bf16.
-// warp 0 TMA · warp 1 MMA issue · warp 2 owns TMEM · warps 4-11 epilogue (two per TMEM lane
-// quadrant, alternate 32-column chunks; thread = one user).  The targets come from a bitmap of the
-// slice built beforehand (fd_bitmap_kernel): walking the CSR rows inside this kernel, as the
-// recommend kernel does, serialises one dependent global load per positive and made two helper
-// warps the pace of the whole kernel at config C's 145 items per user (profiles/r01_j_*).
+// warp 0 TMA · warp 1 MMA issue · warp 2 owns TMEM · warps 4-19 epilogue: four per TMEM lane
+// quadrant, warp (q, h) turns columns 64h..64h+63 of rows 32q..32q+31 into a [32][128-byte]
+// staging tile and hands it to the TMA store engine (whole 128-byte lines reach L2; the first
+// version stored 16 bytes per lane straight from registers and ran the L2 at 62 % with the
+// tensor pipe at 21 %, profiles/r01_k_*).  The targets come from a bitmap of the slice built
+// beforehand (fd_bitmap_kernel): walking the CSR rows inside this kernel, as the recommend kernel
+// does, serialises one dependent global load per positive and made two helper warps the pace of
+// the whole kernel at config C's 145 items per user (profiles/r01_j_*).
 template <int KB, int LT>
-__global__ void __launch_bounds__(384, 1) fd_score_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                          const __grid_constant__ CUtensorMap map_b, ScoreArgs a) {
+__global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                          const __grid_constant__ CUtensorMap map_b,
+                                                          const __grid_constant__ CUtensorMap map_g, ScoreArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                   // KB x [128][64] bf16, swizzled
   unsigned char* sB = sA + KB * A_BLK_BYTES;                  // SC_STAGE x [256][64] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SC_STAGE * B_BLK_BYTES);
+  unsigned char* sG = sB + SC_STAGE * B_BLK_BYTES;            // 16 x [32][64] bf16 staging tiles, swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 16 * SC_STG_BYTES);
   uint64_t* full = bars;                  // [SC_STAGE]
   uint64_t* empty = bars + SC_STAGE;      // [SC_STAGE]
   uint64_t* a_full = bars + 2 * SC_STAGE;
@@ -224,6 +240,7 @@ __global__ void __launch_bounds__(384, 1) fd_score_kernel(const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_g);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SC_STAGE; ++s) {
@@ -233,7 +250,7 @@ __global__ void __launch_bounds__(384, 1) fd_score_kernel(const __grid_constant_
     mbar_init(a_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(t_full + b, 1);
-      mbar_init(t_empty + b, 8);
+      mbar_init(t_empty + b, 16);
     }
     fence_barrier_init();
   }
@@ -287,50 +304,56 @@ __global__ void __launch_bounds__(384, 1) fd_score_kernel(const __grid_constant_
   } else if (warp >= 4) {
     const int e = warp - 4;
     const int q = e & 3;                    // TMEM lane quadrant (= warp % 4)
-    const int hf = e >> 2;                  // chunks hf, hf + 2, ...
+    const int h = e >> 2;                   // columns 64h .. 64h+63 of every tile
     const int row = q * 32 + lane;
     const bool row_ok = u0 + row < a.n_users;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    __nv_bfloat16* grow = a.G + (int64_t)(u0 + row) * a.I_pad;
-    // this row's 256 target bits of a tile are 32 contiguous bytes of the slice's bitmap; the words
-    // of tile t + 1 are fetched while tile t is processed (member hf uses words hf, hf+2, hf+4, hf+6)
-    const uint4* brow = reinterpret_cast<const uint4*>(a.bits + (int64_t)(u0 + row) * (a.I_pad / 32)) + (int64_t)t_lo * 2;
-    uint4 nb0 = make_uint4(0u, 0u, 0u, 0u), nb1 = nb0;
-    if (n_t > 0) { nb0 = __ldg(brow); nb1 = __ldg(brow + 1); }
+    unsigned char* stg = sG + e * SC_STG_BYTES;
+    unsigned char* srow = stg + lane * 128;
+    const int sw = lane & 7;
+    // this row's 64 target bits of a tile are 8 bytes of the slice's bitmap; the words of tile t + 1
+    // are fetched at the END of tile t's work (a load issued before the current words are consumed
+    // would share their scoreboard and stall the consumer)
+    const uint2* brow = reinterpret_cast<const uint2*>(a.bits + (int64_t)(u0 + row) * (a.I_pad / 32)) + (int64_t)t_lo * 4 + h;
+    uint2 nb = make_uint2(0u, 0u);
+    if (n_t > 0) nb = __ldg(brow);
     for (int t = 0; t < n_t; ++t) {
       const int buf = t & 1;
       const uint32_t par = (t >> 1) & 1;
-      const uint4 cb0 = nb0, cb1 = nb1;
-      if (t + 1 < n_t) { nb0 = __ldg(brow + 2 * (t + 1)); nb1 = __ldg(brow + 2 * (t + 1) + 1); }
-      const uint32_t my_bm[4] = {hf ? cb0.y : cb0.x, hf ? cb0.w : cb0.z, hf ? cb1.y : cb1.x, hf ? cb1.w : cb1.z};
+      const uint2 cb = nb;
+      const int64_t item0 = (int64_t)(t_lo + t) * TILE_I + h * 64;
+      const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I + h * 64);
       mbar_wait(t_full + buf, par);
       tc_fence_after();
-      const int64_t item0 = (int64_t)(t_lo + t) * TILE_I;
-      const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I);
-      uint32_t va[32], vb[32];
-      tmem_ld32_issue(col0 + (uint32_t)(hf * 32), va);
-#pragma unroll
-      for (int i = 0; i < 4; i += 2) {
-        const int c0 = hf + i * 2, c1 = hf + (i + 1) * 2;
-        tmem_ld_wait(va);
-        tmem_ld32_issue(col0 + (uint32_t)(c1 * 32), vb);
-        {
-          const int64_t first = item0 + c0 * 32;
-          const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
-          grad_chunk<LT>(va, my_bm[i], valid, row_ok, grow + first);
-        }
-        tmem_ld_wait(vb);
-        if (i + 2 < 4) tmem_ld32_issue(col0 + (uint32_t)((c1 + 2) * 32), va);
-        {
-          const int64_t first = item0 + c1 * 32;
-          const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
-          grad_chunk<LT>(vb, my_bm[i + 1], valid, row_ok, grow + first);
-        }
+      uint32_t v[32];
+      tmem_ld32_issue(col0, v);
+      // the TMA store of the previous tile must have read the staging tile before it is rewritten
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      tmem_ld_wait(v);
+      {
+        const uint32_t valid = item0 + 32 <= a.I ? 0xffffffffu : (item0 >= a.I ? 0u : ((1u << (int)(a.I - item0)) - 1u));
+        grad_chunk<LT>(v, cb.x, valid, row_ok, srow, 0, sw);
       }
+      tmem_ld32_issue(col0 + 32u, v);
+      tmem_ld_wait(v);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + buf);
+      if (lane == 0) mbar_arrive(t_empty + buf);   // this warp's TMEM columns are in registers
+      {
+        const int64_t first = item0 + 32;
+        const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+        grad_chunk<LT>(v, cb.y, valid, row_ok, srow, 4, sw);
+      }
+      fence_proxy_async();                         // staging writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_g, stg, (int)item0, u0 + q * 32);
+        bulk_commit();
+      }
+      if (t + 1 < n_t) nb = __ldg(brow + 4 * (t + 1));
     }
+    if (lane == 0) bulk_wait0();
   }
 
   tc_fence_before();

@@ -6,7 +6,10 @@
 // Layout: all item/user tables are row-major [rows][ld] fp32 with ld = a whole number of
 // 128-byte lines that one <G,NV> geometry covers EXACTLY (ld = 4*G*NV: 32, 64, 96, 128, 192, 256,
 // 384 or 512 floats, row_stride() in api.cu; pad columns are kept at exactly 0), so no kernel
-// needs a column bound check.  A row is owned
+// needs a column bound check for correctness.  gather / scatter skip the 16-byte pieces that lie
+// ENTIRELY in the padding (14 of 64 columns at K = 50, 56 of 256 at K = 200: loads that return 0,
+// reductions that add 0) with a per-lane predicate; in decode_kernel the same predicate costs more
+// issue slots than the L2 transactions it saves (36.3 -> 35.1 M users/s at config B), so it is not used there.  A row is owned
 // by a GROUP of G >= 8 lanes, each holding NV <= 4 float4 (column 4*(v*G+lane) .. +3), so ONE
 // warp-level 16-byte load/reduction covers whole 128-byte lines of 32/G rows.  History
 // (profiles/r01_*): v1 used 224-byte rows with 16 lanes per row and was issue-bound; v2 used 4
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        w[t][v] = it[t] >= 0 ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+        w[t][v] = (it[t] >= 0 && c < m.K) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
       }
 #pragma unroll
     for (int t = 0; t < UNR; ++t)
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        w[t][v] = it[t] >= 0 ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+        w[t][v] = (it[t] >= 0 && c < m.K) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
       }
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, fma4(m.lambda, w[t][v], sd[v]));
+        if (c < m.K) red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, fma4(m.lambda, w[t][v], sd[v]));
         if (m.linear_function) gu[v] = add4(gu[v], mul4(d[v], w[t][v]));
       }
     }
