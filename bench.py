@@ -301,6 +301,9 @@ def run_ours(args):
                 "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
         if world == 1 and not args.no_topn:
             line["topn"] = topn_section(m, U, peak_tf, peak_src)
+        if world == 1 and not args.no_fulldecode:
+            m.close()                                          # free config B before the config-C-shaped run
+            line["fulldecode"] = fulldecode_section(local, peak_tf, peak_src)
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc
             orc.build(ref=False)
@@ -341,6 +344,53 @@ def topn_section(m, U, peak_tf, peak_src):
     return out
 
 
+def fulldecode_section(device, peak_burst, peak_src):
+    """Secondary measurement: full-item-decode TRAINING (BASELINE.json configs[2]:
+    138K x 27K, K=200, full-item decode, 1xB200) — the three tcgen05 contractions of
+    csrc/fulldec_tc.cuh inside the complete training step.  Bounded to the first 4 frozen
+    minibatches' worth of users of that shape (128 x SM count users each) so the default bench run
+    stays short; per-user cost does not depend on U."""
+    from cdae_b200 import CDAE, CDAEConfig, synth
+    import torch
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    Uc, Ic, Kc, mean = 4 * 128 * sms, 27_000, 200, 145.0
+    d = synth.make_dataset(Uc, Ic, mean_train=mean, seed=SEED)
+    cfg = CDAEConfig(lambda_=0.01, learn_rate=0.1, corruption_ratio=0.5, beta=1.0, loss="CE", num_dim=Kc,
+                     using_adagrad=True, asymmetric=True, user_factor=True, scaled=True,
+                     full_decode=True, device=device)
+    m = CDAE(cfg).reset(Uc, Ic, d["train_row_ptr"], d["train_col"])
+    m.init_params(SEED)
+    for ep in range(2):
+        m.train_one_iteration(seed=SEED, epoch=ep)
+    m.profile(True)
+    reps, ms = 3, []
+    for ep in range(2, 2 + reps):
+        ms.append(m.train_one_iteration(seed=SEED, epoch=ep).device_ms)
+    prof = m.profile_get()
+    m.profile(False)
+    m.close()
+    per = {k: v[0] / reps for k, v in prof.items() if v[1]}
+    tens_ms = per["fd_score"] + per["fd_hidden"] + per["fd_itemgrad"]
+    flops = 6.0 * Uc * Ic * Kc                                 # SURVEY 8d: 6*I*K per user
+    d_peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak_sus = float(d_peaks.get("bf16_tflops_sustained", 1400.0))
+    step_ms = float(np.median(ms))
+    ach = flops / (tens_ms / 1e3) / 1e12
+    return {"what": "CDAE training with full-item decode (targets 1 on the train row, 0 elsewhere), bf16 tcgen05, fp32 accumulate",
+            "workload": "config C shape: %d users (4 minibatches of 128 x %d SMs; BASELINE's 138K bounded) x %d items, K=%d, mean %d train items/user, asymmetric, CE, AdaGrad"
+                        % (Uc, sms, Ic, Kc, int(mean)),
+            "users_per_s": Uc / (step_ms / 1e3), "ms_per_epoch": step_ms,
+            "kernel_ms_per_epoch": per,
+            "roofline": {"bound": "tensor", "kernel": "fd_score_kernel + fd_gemm_kernel<hidden> + fd_gemm_kernel<itemgrad>",
+                         "achieved": ach, "peak": peak_sus,
+                         "peak_source": peak_src + ", sustained (timed inside a long step)",
+                         "unit": "TFLOP/s", "frac": ach / peak_sus,
+                         "flops": "6*U*I*K (SURVEY 8d)", "peak_burst": peak_burst,
+                         "per_kernel_tflops": {k: (flops / 3.0) / (per[k] / 1e3) / 1e12 for k in ("fd_score", "fd_hidden", "fd_itemgrad")},
+                         "whole_step_tflops": flops / (step_ms / 1e3) / 1e12,
+                         "traffic": ncu_traffic("fd_gemm_kernel")[0]}}
+
+
 class OneLineStdout:
     """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints
     "NCCL version ..." from C code at communicator init), so file descriptor 1 is pointed at stderr
@@ -376,6 +426,7 @@ def main():
                     help="users in the bounded CPU-baseline sample (about 10-15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-topn", action="store_true", help="skip the recommend (full-item decode) section")
+    ap.add_argument("--no-fulldecode", action="store_true", help="skip the full-item-decode training section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1,6 +1,7 @@
 // cdae_b200/csrc/fulldec_api.inl — host side of full-item-decode training (fulldec_tc.cuh),
 // included at the end of api.cu.  One frozen minibatch:
-//   pack (W' + b' -> Wb, Z -> Zb)  ->  fd_score (G)  ->  fd_gemm<hidden> (HG)  ->  fd_gemm<itemgrad> (gW', gb')
+//   pack (W' + b' -> Wb, Z -> Zb, targets -> bitmap)  ->  fd_fused (G, HG)  ->  fd_gemm<itemgrad> (gW', gb')
+//   [CDAE_B200_FD=split: fd_score (G) -> fd_gemm<hidden> (HG) -> fd_gemm<itemgrad>]
 // in place of decode_kernel; everything before (gather, activate) and after (hidden_backward,
 // scatter, all-reduce, apply) is the sampled path's.
 
@@ -47,6 +48,18 @@ static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorM
   fd::fd_gemm_kernel<KB, ITEMGRAD><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
   return 0;
 }
+template <int KB, int LT>
+static int fd_launch_fused(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mg,
+                           const fd::FusedArgs& a, dim3 grid) {
+  static bool attr_set = false;
+  const size_t dyn = fd::fused_smem(KB);
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(fd::fd_fused_kernel<KB, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  fd::fd_fused_kernel<KB, LT><<<grid, 640, dyn, h->stream>>>(ma, mw, mg, a);
+  return 0;
+}
 #define FD_DISPATCH_KB(KBV, CALL)      \
   switch (KBV) {                       \
     case 1: TRY(CALL(1)); break;       \
@@ -90,6 +103,29 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   TRY(tc_make_map(&m_wb_mn, wb, (uint64_t)I_pad, (uint64_t)Kp, 64));           // hidden: B = Wb, {64 cols, 64 items}
   TRY(tc_make_map(&m_zb_mn, zb, (uint64_t)B_pad, (uint64_t)Kp, 64));           // itemgrad: B = Zb, {64 cols, 64 users}
   const int u_tiles = (int)(B_pad / 128);
+  // CDAE_B200_FD=split keeps the score and hidden-gradient contractions in separate launches (A/B runs)
+  static const bool split_path = getenv("CDAE_B200_FD") && strcmp(getenv("CDAE_B200_FD"), "split") == 0;
+  if (!split_path) {
+    fd::FusedArgs a;
+    a.n_users = bt.n_users; a.I = h->I; a.I_pad = I_pad; a.n_tiles = (int)(I_pad / fd::FU_TILE_I);
+    a.ksteps = (K + 2 + 15) / 16; a.K = K; a.ld = h->ld;
+    a.bits = h->fd_bits.p; a.HG = bt.HG;
+    a.outputs = &h->stats_d->outputs[0];
+    const int S = fd_pick_split(u_tiles, a.n_tiles, 16, h->sm_count, 32);
+    a.tiles_per_split = (a.n_tiles + S - 1) / S;
+    const dim3 grid(u_tiles, (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    ProfScope ps(h, CDAE_K_FD_SCORE);
+    if (h->m.loss == LOSS_CE) {
+#define CALL(KBV) fd_launch_fused<KBV, LOSS_CE>(h, m_zb_a, m_wb_mn, m_g_rows, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    } else {
+#define CALL(KBV) fd_launch_fused<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_mn, m_g_rows, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    }
+    KERNEL_OK(h);
+  } else {
   {
     fd::ScoreArgs a;
     a.n_users = bt.n_users; a.I = h->I; a.I_pad = I_pad; a.n_tiles = (int)(I_pad / tc::TILE_I);
@@ -124,6 +160,7 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     KERNEL_OK(h);
+  }
   }
   {
     fd::GemmArgs a{};

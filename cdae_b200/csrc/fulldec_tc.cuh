@@ -365,6 +365,227 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused score + hidden-gradient kernel.  fd_score_kernel is paced by its epilogue (one MUFU and ~12
+// issue slots per score against 0.05 clk of tensor time), so the tensor pipe idles 80 % of the time,
+// while the separate HG = G W' launch re-reads all of G from HBM.  Here the SAME CTA that turns a
+// 128 x 64 score tile into loss gradients hands that tile — already in shared memory as a K-major
+// UMMA operand, because that is also the layout the TMA store wants — straight back to the tensor
+// core: HG[128 x Kp] += G_tile[128 x 64] . W'_tile[64 x Kp], with W'_tile the very k-blocks the
+// first contraction just used, re-read MN-major.  The second contraction hides completely under
+// the epilogue; G still goes out once (for the item gradient), but is read once instead of twice.
+//
+//   per 64-item tile t (slot = t % 3, s = t & 1):
+//     TMA      W' tile -> slot                         (KB boxes {64 k, 64 items}, 8 KB each)
+//     MMA      S[s]  = Zb . W'_tile^T                  (N = 64; 128 x 64 fp32 in TMEM columns 64 s ..)
+//     epilogue set s (8 warps): S[s] -> g -> bf16 -> Gs[s] (shared, swizzled) -> TMA store to G
+//     MMA      HG   += Gs[s] . W'_tile                 (N = Kp; TMEM columns 128 .. 128 + Kp)
+//   the two epilogue sets work on alternate tiles, so both S buffers / G buffers are in flight.
+// warp 0 TMA · warp 1 MMA issue · warp 2 owns TMEM · warps 4-19 epilogue: warp = (set s, quadrant
+// q, half h) handles rows 32q.., columns 32h.. of the tiles with t & 1 == s.
+constexpr int FU_TILE_I = 64;
+constexpr int FU_SLOTS = 3;
+constexpr int FU_G_BYTES = 128 * 128;                 // one G tile: [128 users][64 items] bf16
+__host__ __device__ constexpr size_t fused_smem(int kb) {
+  return 1024 + (size_t)kb * A_BLK_BYTES + (size_t)FU_SLOTS * kb * GM_BOX_BYTES + 2 * FU_G_BYTES + 256;
+}
+
+struct FusedArgs {
+  int n_users;
+  int64_t I, I_pad;
+  int n_tiles;               // I_pad / 64
+  int tiles_per_split;
+  int ksteps;                // ceil((K + 2) / 16)
+  int K, ld;
+  const uint32_t* bits;      // [B_pad][I_pad / 32]
+  float* HG;                 // [n_users][ld], zero or partial sums (reduced into)
+  unsigned long long* outputs;
+};
+
+template <int KB, int LT>
+__global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                          const __grid_constant__ CUtensorMap map_w,
+                                                          const __grid_constant__ CUtensorMap map_g, FusedArgs a) {
+  constexpr int NCOL = KB * KBLK;                 // Kp
+  constexpr int W_TILE_BYTES = KB * GM_BOX_BYTES;
+  constexpr uint32_t HG_COL = 128;                // TMEM column of the HG accumulator
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                   // KB x [128][64] bf16
+  unsigned char* sW = sA + KB * A_BLK_BYTES;                  // FU_SLOTS x KB x [64][64] bf16
+  unsigned char* sG = sW + FU_SLOTS * W_TILE_BYTES;           // 2 x [128][64] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * FU_G_BYTES);
+  uint64_t* w_full = bars;                 // [3]
+  uint64_t* w_empty = bars + 3;            // [3]
+  uint64_t* a_full = bars + 6;
+  uint64_t* t_full = bars + 7;             // [2] scores ready
+  uint64_t* t_empty = bars + 9;            // [2] scores in registers
+  uint64_t* g_full = bars + 11;            // [2] gradient tile written
+  uint64_t* g_empty = bars + 13;           // [2] gradient tile consumed by the second contraction
+  uint64_t* hg_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TILE_U;
+  const int t_lo = blockIdx.y * a.tiles_per_split;
+  const int n_t = max(0, min(a.n_tiles, t_lo + a.tiles_per_split) - t_lo);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_g);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(w_full + i, 1);
+      mbar_init(w_empty + i, 1);
+    }
+    mbar_init(a_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full + b, 1);
+      mbar_init(t_empty + b, 8);
+      mbar_init(g_full + b, 1);
+      mbar_init(g_empty + b, 1);
+    }
+    mbar_init(hg_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && a.outputs)
+    atomicAdd(a.outputs, (unsigned long long)a.n_users * (unsigned long long)a.I);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_t > 0) {
+      mbar_arrive_expect_tx(a_full, KB * A_BLK_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_BLK_BYTES, &map_a, a_full, kb * KBLK, u0);
+      for (int t = 0; t < n_t; ++t) {
+        const int slot = t % FU_SLOTS;
+        mbar_wait(w_empty + slot, ((t / FU_SLOTS) & 1) ^ 1);
+        mbar_arrive_expect_tx(w_full + slot, W_TILE_BYTES);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(sW + slot * W_TILE_BYTES + kb * GM_BOX_BYTES, &map_w, w_full + slot, kb * KBLK, (t_lo + t) * FU_TILE_I);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_t > 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(TILE_U, FU_TILE_I);                 // S: both K-major
+      constexpr uint32_t idesc2 = umma_idesc_bf16_major(TILE_U, NCOL, 0, 1);          // HG: B MN-major
+      mbar_wait(a_full, 0);
+      // first contraction of tile t
+      auto scores = [&](int t) {
+        const int sb = t & 1, slot = t % FU_SLOTS;
+        mbar_wait(t_empty + sb, ((t >> 1) & 1) ^ 1);
+        mbar_wait(w_full + slot, (t / FU_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(sb * FU_TILE_I);
+        const uint32_t w0 = smem_u32(sW + slot * W_TILE_BYTES);
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t a0 = smem_u32(sA + kb * A_BLK_BYTES), b0 = w0 + kb * GM_BOX_BYTES;
+          const int nk = min(KBLK / 16, a.ksteps - kb * (KBLK / 16));
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc1, (kb | k) != 0);
+        }
+        umma_commit(t_full + sb);
+      };
+      scores(0);
+      if (n_t > 1) scores(1);
+      for (int t = 0; t < n_t; ++t) {
+        const int sb = t & 1, slot = t % FU_SLOTS;
+        mbar_wait(g_full + sb, (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t g0 = smem_u32(sG + sb * FU_G_BYTES), w0 = smem_u32(sW + slot * W_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < FU_TILE_I / 16; ++k)
+          umma_bf16(tmem_base + HG_COL, umma_desc_sw128(g0 + k * 32), umma_desc_mn_sw128(w0 + k * 2048, GM_BOX_BYTES),
+                    idesc2, (t | k) != 0);
+        umma_commit(g_empty + sb);
+        umma_commit(w_empty + slot);
+        if (t + 2 < n_t) scores(t + 2);
+      }
+      umma_commit(hg_full);
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = e & 3;                    // TMEM lane quadrant (= warp % 4)
+    const int h = (e >> 2) & 1;             // columns 32h .. 32h+31 of the tile
+    const int sb = e >> 3;                  // tiles with t & 1 == sb
+    const int row = q * 32 + lane;
+    const bool row_ok = u0 + row < a.n_users;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    unsigned char* gt = sG + sb * FU_G_BYTES;
+    unsigned char* srow = gt + row * 128;
+    const int sw = row & 7;
+    const bool leader = (e & 7) == 0 && lane == 0;       // one thread per set talks to the MMA warp / TMA
+    const uint32_t* brow = a.bits + (int64_t)(u0 + row) * (a.I_pad / 32) + (int64_t)t_lo * 2 + h;
+    uint32_t nb = 0u;
+    if (sb < n_t) nb = __ldg(brow + 2 * sb);
+    for (int t = sb; t < n_t; t += 2) {
+      const uint32_t par = (t >> 1) & 1;
+      const uint32_t cb = nb;
+      const int64_t item0 = (int64_t)(t_lo + t) * FU_TILE_I;
+      mbar_wait(t_full + sb, par);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32_issue(lane_addr + (uint32_t)(sb * FU_TILE_I + h * 32), v);
+      tmem_ld_wait(v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + sb);
+      // the gradient tile of tile t - 2 must have been read by the second contraction and the TMA store
+      mbar_wait(g_empty + sb, par ^ 1);
+      if (leader) bulk_wait_read0();
+      named_bar_sync(1 + sb, 256);
+      {
+        const int64_t first = item0 + h * 32;
+        const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+        grad_chunk<LT>(v, cb, valid, row_ok, srow, h * 4, sw);
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + sb, 256);
+      if (leader) {
+        mbar_arrive(g_full + sb);
+        tma_store_2d(&map_g, gt, (int)item0, u0);
+        bulk_commit();
+      }
+      if (t + 2 < n_t) nb = __ldg(brow + 2 * (t + 2));
+    }
+    if (leader) bulk_wait0();
+    // ---- hidden gradient of this CTA's item range: thread = user row, warps of a quadrant share the columns
+    if (n_t > 0) {
+      mbar_wait(hg_full, 0);
+      tc_fence_after();
+      const int part = e >> 2;              // 0..3
+      for (int c = part; c * 32 < a.K; c += 4) {
+        uint32_t v[32];
+        tmem_ld32_issue(lane_addr + HG_COL + (uint32_t)(c * 32), v);
+        tmem_ld_wait(v);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = c * 32 + j;
+          if (col >= a.K) break;
+          float x[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col + i >= a.K) x[i] = 0.f;                    // bias columns: not part of the row
+          red_add_v4(a.HG + (int64_t)(u0 + row) * a.ld + col, make_float4(x[0], x[1], x[2], x[3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 struct GemmArgs {
   int n_steps;          // contraction steps of 64 (items for the hidden gradient, users for the item gradient)
   int steps_per_split;  // gridDim.y CTAs share the contraction; partial sums meet in 16-byte reductions
@@ -512,5 +733,5 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
 
 }  // namespace fd
 }  // namespace cdae
-static_assert(cdae::fd::score_smem(4) <= 232448 && cdae::fd::gemm_smem(4) <= 232448,
+static_assert(cdae::fd::score_smem(4) <= 232448 && cdae::fd::gemm_smem(4) <= 232448 && cdae::fd::fused_smem(4) <= 232448,
               "full-decode kernels exceed the 227 KB of shared memory a CTA can opt into");
