@@ -1,7 +1,7 @@
 // cdae_b200/csrc/fulldec_api.inl — host side of full-item-decode training (fulldec_tc.cuh),
 // included at the end of api.cu.  One frozen minibatch:
-//   pack (W' + b' -> Wb, Z -> Zb, targets -> bitmap)  ->  fd_fused (G, HG)  ->  fd_gemm<itemgrad> (gW', gb')
-//   [CDAE_B200_FD=split: fd_score (G) -> fd_gemm<hidden> (HG) -> fd_gemm<itemgrad>]
+//   pack (W' + b' -> Wb, Z -> Zb, targets -> bitmap)  ->  fd_score (G)  ->  fd_gemm<hidden> (HG)  ->  fd_gemm<itemgrad> (gW', gb')
+//   [CDAE_B200_FD=fused: fd_fused (G, HG) -> fd_gemm<itemgrad>]
 // in place of decode_kernel; everything before (gather, activate) and after (hidden_backward,
 // scatter, all-reduce, apply) is the sampled path's.
 
@@ -103,9 +103,13 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   TRY(tc_make_map(&m_wb_mn, wb, (uint64_t)I_pad, (uint64_t)Kp, 64));           // hidden: B = Wb, {64 cols, 64 items}
   TRY(tc_make_map(&m_zb_mn, zb, (uint64_t)B_pad, (uint64_t)Kp, 64));           // itemgrad: B = Zb, {64 cols, 64 users}
   const int u_tiles = (int)(B_pad / 128);
-  // CDAE_B200_FD=split keeps the score and hidden-gradient contractions in separate launches (A/B runs)
-  static const bool split_path = getenv("CDAE_B200_FD") && strcmp(getenv("CDAE_B200_FD"), "split") == 0;
-  if (!split_path) {
+  // CDAE_B200_FD=fused: score + hidden-gradient contraction in ONE kernel (fd_fused_kernel).  Parity-
+  // identical; measured 9 % slower than the two launches at config C (its W' tiles stay in shared
+  // memory from the first contraction to the second, which leaves too few slots to hide the TMA
+  // latency under the ~42 B/clk/SM the L2 can deliver when every SM streams W': profiles/r01_m_*),
+  // so the split path is the default.
+  static const bool fused_path = getenv("CDAE_B200_FD") && strcmp(getenv("CDAE_B200_FD"), "fused") == 0;
+  if (fused_path) {
     fd::FusedArgs a;
     a.n_users = bt.n_users; a.I = h->I; a.I_pad = I_pad; a.n_tiles = (int)(I_pad / fd::FU_TILE_I);
     a.ksteps = (K + 2 + 15) / 16; a.K = K; a.ld = h->ld;

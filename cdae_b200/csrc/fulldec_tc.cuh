@@ -160,9 +160,8 @@ struct ScoreArgs {
 // staging tile ([32 rows][128 bytes], 128-byte swizzled like every TMA tile: 16-byte piece c of
 // row r lives at piece c ^ (r & 7)); cbase = 0 / 4 selects the half of the row.
 template <int LT>
-__device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
-                                           unsigned char* srow, int cbase, int sw) {
-  uint32_t o[16];
+__device__ __forceinline__ void grad_compute(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
+                                             uint32_t (&o)[16]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     const float y0 = __uint_as_float(v[j]), y1 = __uint_as_float(v[j + 1]);
@@ -191,9 +190,18 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = 0u;
   }
+}
+__device__ __forceinline__ void grad_store(const uint32_t (&o)[16], unsigned char* srow, int cbase, int sw) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(srow + (((cbase + j) ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+template <int LT>
+__device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
+                                           unsigned char* srow, int cbase, int sw) {
+  uint32_t o[16];
+  grad_compute<LT>(v, pos, valid, row_ok, o);
+  grad_store(o, srow, cbase, sw);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -380,10 +388,11 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
 //     epilogue set s (8 warps): S[s] -> g -> bf16 -> Gs[s] (shared, swizzled) -> TMA store to G
 //     MMA      HG   += Gs[s] . W'_tile                 (N = Kp; TMEM columns 128 .. 128 + Kp)
 //   the two epilogue sets work on alternate tiles, so both S buffers / G buffers are in flight.
-// warp 0 TMA · warp 1 MMA issue · warp 2 owns TMEM · warps 4-19 epilogue: warp = (set s, quadrant
-// q, half h) handles rows 32q.., columns 32h.. of the tiles with t & 1 == s.
+// warp 0 TMA loads · warp 1 MMA issue · warp 2 owns TMEM · warp 3 TMA stores of G · warps 4-19
+// epilogue: warp = (set s, quadrant q, half h) handles rows 32q.., columns 32h.. of the tiles with
+// t & 1 == s.  All hand-offs are mbarriers (no CTA-wide or set-wide bar.sync in the tile loop).
 constexpr int FU_TILE_I = 64;
-constexpr int FU_SLOTS = 3;
+constexpr int FU_SLOTS = 4;                           // W' tiles in flight: t (2nd contraction) .. t + 3 (landing)
 constexpr int FU_G_BYTES = 128 * 128;                 // one G tile: [128 users][64 items] bf16
 __host__ __device__ constexpr size_t fused_smem(int kb) {
   return 1024 + (size_t)kb * A_BLK_BYTES + (size_t)FU_SLOTS * kb * GM_BOX_BYTES + 2 * FU_G_BYTES + 256;
@@ -414,15 +423,16 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
   unsigned char* sW = sA + KB * A_BLK_BYTES;                  // FU_SLOTS x KB x [64][64] bf16
   unsigned char* sG = sW + FU_SLOTS * W_TILE_BYTES;           // 2 x [128][64] bf16
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * FU_G_BYTES);
-  uint64_t* w_full = bars;                 // [3]
-  uint64_t* w_empty = bars + 3;            // [3]
-  uint64_t* a_full = bars + 6;
-  uint64_t* t_full = bars + 7;             // [2] scores ready
-  uint64_t* t_empty = bars + 9;            // [2] scores in registers
-  uint64_t* g_full = bars + 11;            // [2] gradient tile written
-  uint64_t* g_empty = bars + 13;           // [2] gradient tile consumed by the second contraction
-  uint64_t* hg_full = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* w_full = bars;                 // [FU_SLOTS]
+  uint64_t* w_empty = bars + FU_SLOTS;     // [FU_SLOTS]
+  uint64_t* a_full = bars + 2 * FU_SLOTS;
+  uint64_t* t_full = a_full + 1;           // [2] scores ready
+  uint64_t* t_empty = t_full + 2;          // [2] scores in registers
+  uint64_t* g_full = t_empty + 2;          // [2] gradient tile written
+  uint64_t* g_empty = g_full + 2;          // [2] gradient tile consumed by the second contraction
+  uint64_t* hg_full = g_empty + 2;
+  uint64_t* s_free = hg_full + 1;          // [2] gradient tile read by the TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * TILE_U;
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
     tma_prefetch_desc(&map_g);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < FU_SLOTS; ++i) {
       mbar_init(w_full + i, 1);
       mbar_init(w_empty + i, 1);
     }
@@ -443,8 +453,9 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       mbar_init(t_full + b, 1);
       mbar_init(t_empty + b, 8);
-      mbar_init(g_full + b, 1);
+      mbar_init(g_full + b, 8);       // one arrive per epilogue warp of the set
       mbar_init(g_empty + b, 1);
+      mbar_init(s_free + b, 1);
     }
     mbar_init(hg_full, 1);
     fence_barrier_init();
@@ -494,6 +505,10 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
       if (n_t > 1) scores(1);
       for (int t = 0; t < n_t; ++t) {
         const int sb = t & 1, slot = t % FU_SLOTS;
+        // scores of tile t + 2 go in FIRST: they only need S[sb] to be in the epilogue's registers
+        // (early in its work on tile t), and must be ready when that set comes back for more; the
+        // second contraction of tile t is needed by nobody for two more tiles
+        if (t + 2 < n_t) scores(t + 2);
         mbar_wait(g_full + sb, (t >> 1) & 1);
         tc_fence_after();
         const uint32_t g0 = smem_u32(sG + sb * FU_G_BYTES), w0 = smem_u32(sW + slot * W_TILE_BYTES);
@@ -503,9 +518,21 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
                     idesc2, (t | k) != 0);
         umma_commit(g_empty + sb);
         umma_commit(w_empty + slot);
-        if (t + 2 < n_t) scores(t + 2);
       }
       umma_commit(hg_full);
+    }
+  } else if (warp == 3) {
+    // ===== G store: as soon as a gradient tile is complete it goes out through the TMA engine
+    if (lane == 0) {
+      for (int t = 0; t < n_t; ++t) {
+        const int sb = t & 1;
+        mbar_wait(g_full + sb, (t >> 1) & 1);
+        tma_store_2d(&map_g, sG + sb * FU_G_BYTES, (t_lo + t) * FU_TILE_I, u0);
+        bulk_commit();
+        bulk_wait_read0();                  // the engine has read the tile out of shared memory
+        mbar_arrive(s_free + sb);
+      }
+      bulk_wait0();
     }
   } else if (warp >= 4) {
     const int e = warp - 4;
@@ -518,7 +545,6 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
     unsigned char* gt = sG + sb * FU_G_BYTES;
     unsigned char* srow = gt + row * 128;
     const int sw = row & 7;
-    const bool leader = (e & 7) == 0 && lane == 0;       // one thread per set talks to the MMA warp / TMA
     const uint32_t* brow = a.bits + (int64_t)(u0 + row) * (a.I_pad / 32) + (int64_t)t_lo * 2 + h;
     uint32_t nb = 0u;
     if (sb < n_t) nb = __ldg(brow + 2 * sb);
@@ -534,25 +560,23 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + sb);
-      // the gradient tile of tile t - 2 must have been read by the second contraction and the TMA store
-      mbar_wait(g_empty + sb, par ^ 1);
-      if (leader) bulk_wait_read0();
-      named_bar_sync(1 + sb, 256);
+      // the gradient tile of tile t - 2 must have been read by the second contraction and by the
+      // TMA store before it is overwritten (checked AFTER the arithmetic, when both are long done);
+      // no warp waits for its siblings — each one publishes its 32 x 32 block and moves on
+      uint32_t o[16];
       {
         const int64_t first = item0 + h * 32;
         const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
-        grad_chunk<LT>(v, cb, valid, row_ok, srow, h * 4, sw);
+        grad_compute<LT>(v, cb, valid, row_ok, o);
       }
-      fence_proxy_async();
-      named_bar_sync(1 + sb, 256);
-      if (leader) {
-        mbar_arrive(g_full + sb);
-        tma_store_2d(&map_g, gt, (int)item0, u0);
-        bulk_commit();
-      }
+      mbar_wait(g_empty + sb, par ^ 1);
+      mbar_wait(s_free + sb, par ^ 1);
+      grad_store(o, srow, h * 4, sw);
+      fence_proxy_async();                  // generic-proxy writes -> visible to UMMA and TMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_full + sb);
       if (t + 2 < n_t) nb = __ldg(brow + 2 * (t + 2));
     }
-    if (leader) bulk_wait0();
     // ---- hidden gradient of this CTA's item range: thread = user row, warps of a quadrant share the columns
     if (n_t > 0) {
       mbar_wait(hg_full, 0);
