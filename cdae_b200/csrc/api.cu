@@ -435,10 +435,15 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleA
   a.nseg = 0;
   a.lr = h->m.lr; a.beta = h->m.beta; a.adagrad = h->m.adagrad; a.g_steps = h->m.g_steps;
   a.steps_slot = h->m.steps_slot;
-  a.seg[a.nseg++] = ApplySeg{h->m.W, h->m.W_ag, h->m.gW, h->I * h->ld / 4, 0.f};
-  if (h->m.asym) a.seg[a.nseg++] = ApplySeg{h->m.V, h->m.V_ag, h->m.gV, h->I * h->ld / 4, 0.f};
-  a.seg[a.nseg++] = ApplySeg{h->m.bp, h->m.bp_ag, h->m.gbp, h->I4 / 4, 0.f};
-  a.seg[a.nseg++] = ApplySeg{h->m.b, h->m.b_ag, h->m.gb, h->ld / 4, h->m.lambda};
+  // the encoder rows' lambda terms: lambda * (occurrences as a kept input) * W[j], counted by scatter_kernel
+  // (tied full decode: fd_gemm_kernel already added n*lambda*W[j] for every item, the counters stay 0)
+  a.seg[a.nseg++] = ApplySeg{h->m.W, h->m.W_ag, h->m.gW, h->I * h->ld / 4, 0.f,
+                             h->m.gcnt + (int64_t)h->m.steps_slot * h->I4, h->m.lambda, h->ld / 4};
+  if (h->m.asym) a.seg[a.nseg++] = ApplySeg{h->m.V, h->m.V_ag, h->m.gV, h->I * h->ld / 4, 0.f, nullptr, 0.f, 1};
+  a.seg[a.nseg++] = ApplySeg{h->m.bp, h->m.bp_ag, h->m.gbp, h->I4 / 4, 0.f, nullptr, 0.f, 1};
+  a.seg[a.nseg++] = ApplySeg{h->m.b, h->m.b_ag, h->m.gb, h->ld / 4, h->m.lambda, nullptr, 0.f, 1};
+  a.cnt_clear = h->m.gcnt + (int64_t)(h->m.steps_slot ^ 1) * h->I4;
+  a.n_cnt = h->I4;
   apply_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(a);
   KERNEL_OK(h);
   h->m.steps_slot ^= 1;  // apply cleared the other slot for the next minibatch
@@ -573,14 +578,16 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
     if ((rc = alloc_table(h, &m.b_ag, 1, h->K, h->ld, 1e-4f))) break;
     if ((rc = alloc_table(h, &m.bp, 1, (int)I, (int)h->I4, 0.f))) break;
     if ((rc = alloc_table(h, &m.bp_ag, 1, (int)I, (int)h->I4, 1e-4f))) break;
-    // one contiguous gradient buffer: [gW | gV | gb' | gb | steps]
-    h->grad_floats = (size_t)(I * h->ld) * (cfg->asymmetric ? 2 : 1) + (size_t)h->I4 + (size_t)h->ld + 4;
+    // one contiguous gradient buffer: [gW | gV | gb' | input-occurrence counts x2 | gb | steps]
+    h->grad_floats = (size_t)(I * h->ld) * (cfg->asymmetric ? 2 : 1) + 3 * (size_t)h->I4 + (size_t)h->ld + 4;
     if ((rc = ensure(h, h->grad, h->grad_floats))) break;
     if (cudaMemsetAsync(h->grad.p, 0, sizeof(float) * h->grad_floats, h->stream) != cudaSuccess) { rc = set_error(CDAE_E_CUDA, "memset"); break; }
     float* g = h->grad.p;
     m.gW = g; g += I * h->ld;
     if (cfg->asymmetric) { m.gV = g; g += I * h->ld; }
     m.gbp = g; g += h->I4;
+    m.gcnt = g; g += 2 * h->I4;
+    m.I4 = h->I4;
     m.gb = g; g += h->ld;
     m.g_steps = g;
     // CSR

@@ -31,6 +31,9 @@ struct ModelDev {
   float *W_ag, *V_ag, *Wu_ag, *b_ag, *bp_ag, *Uu_ag;
   // dense gradient accumulators of one minibatch (one contiguous buffer, all-reduced as one)
   float *gW, *gV, *gbp, *gb;
+  float* gcnt;     // [2][I4] how often item j was a kept input in this minibatch (the lambda*W[j] terms of
+                   // cdae.hpp:333-349 are added as lambda*count*W[j] by apply_kernel); slot = minibatch parity
+  int64_t I4;
   float* g_steps;  // [2] user steps that contributed (n*lambda*b term); slot = minibatch parity
   int steps_slot;
   int64_t I, U;
@@ -450,6 +453,9 @@ __global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchD
 // H8 item part, cdae.hpp:333-349: every kept input row j gets
 // gW[j] += scale*([Uu[u] (.)] delta) + lambda*W[j]; with linear_function also
 // GU[u] += delta (.) W[j] (:340).  One warp per input chunk, same geometry as gather_kernel.
+// The lambda*W[j] term needs no row read here: the kernel counts the occurrences of j
+// (gcnt[j] += 1) and apply_kernel, which loads W[j] anyway, adds lambda*count*W[j] — that removes
+// half of this kernel's L2 traffic (it is bound by L2 transactions: row reads + 16-byte reductions).
 template <int G, int NV>
 __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
   using RM = RowMap<G, NV>;
@@ -460,6 +466,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
   const WorkItem wi = load_item(bt.in_items + warp);
   const int32_t* items = bt.col + wi.s0;
   const uint8_t* keep = bt.keep + wi.aux0;
+  float* cnt = m.gcnt + (int64_t)m.steps_slot * m.I4;
+  const bool count = m.lambda != 0.f;
   float4 d[NV], sd[NV], gu[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -476,23 +484,26 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
       const int r = base + t * NG + grp;
       it[t] = (r < wi.n && keep[r]) ? __ldg(items + r) : -1;
     }
-    float4 w[UNR][NV];
+    if (m.linear_function) {
 #pragma unroll
-    for (int t = 0; t < UNR; ++t)
+      for (int t = 0; t < UNR; ++t) {
+        if (it[t] < 0) continue;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = RM::col4(gl, v);
-        w[t][v] = (it[t] >= 0 && c < m.K) ? ld4(m.W + (int64_t)it[t] * m.ld + c) : f4zero();
+        for (int v = 0; v < NV; ++v) {
+          const int c = RM::col4(gl, v);
+          if (c < m.K) gu[v] = add4(gu[v], mul4(d[v], ld4(m.W + (int64_t)it[t] * m.ld + c)));
+        }
       }
+    }
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
       if (it[t] < 0) continue;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        if (c < m.K) red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, fma4(m.lambda, w[t][v], sd[v]));
-        if (m.linear_function) gu[v] = add4(gu[v], mul4(d[v], w[t][v]));
+        if (c < m.K) red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, sd[v]);
       }
+      if (count && gl == 0) red_add_f32(cnt + it[t], 1.f);
     }
   }
   if (m.linear_function) {
@@ -533,6 +544,9 @@ struct ApplySeg {
   float *w, *acc, *g;
   int64_t n4;        // float4 count
   float extra_coef;  // b only: g += extra_coef * n_steps * w   (n * lambda * b)
+  const float* cnt;  // W only: g[row] += cnt_coef * cnt[row] * w[row]   (lambda * occurrences * W[j])
+  float cnt_coef;
+  int ld4;           // float4 per row (cnt != nullptr)
 };
 struct ApplyArgs {
   ApplySeg seg[4];
@@ -541,23 +555,29 @@ struct ApplyArgs {
   int adagrad;
   float* g_steps;  // [2]: read slot `steps_slot`, clear the other one for the next minibatch
   int steps_slot;
+  float* cnt_clear;  // the occurrence counters of the OTHER slot (consumed by the previous apply)
+  int64_t n_cnt;
 };
 __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
   const float steps = a.g_steps[a.steps_slot];
   if (blockIdx.x == 0 && threadIdx.x == 0) a.g_steps[a.steps_slot ^ 1] = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_cnt / 4; i += (int64_t)gridDim.x * blockDim.x)
+    st4(a.cnt_clear + i * 4, f4zero());
   for (int s = 0; s < a.nseg; ++s) {
     const ApplySeg sg = a.seg[s];
     const float extra = sg.extra_coef * steps;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n4;
          i += (int64_t)gridDim.x * blockDim.x) {
       float4 g4 = ld4(sg.g + i * 4);
-      if (extra == 0.f && g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) continue;
+      const float rowc = sg.cnt ? sg.cnt_coef * __ldg(sg.cnt + i / sg.ld4) : 0.f;
+      if (extra == 0.f && rowc == 0.f && g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) continue;
       float4 w4 = ld4(sg.w + i * 4);
       float g[4] = {g4.x, g4.y, g4.z, g4.w};
       float w[4] = {w4.x, w4.y, w4.z, w4.w};
-      if (extra != 0.f) {
+      const float lin = extra + rowc;
+      if (lin != 0.f) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) g[k] += extra * w[k];
+        for (int k = 0; k < 4; ++k) g[k] += lin * w[k];
       }
       if (a.adagrad) {
         float4 a4 = ld4(sg.acc + i * 4);
