@@ -64,6 +64,7 @@ struct CDAEConfig {
   // device options (no reference counterpart); 0 = engine default / environment
   size_t batch_users = 0;
   int device = -1;
+  bool full_decode = false;   // decode against ALL items on tcgen05 (num_neg ignored); env CDAE_B200_FULL_DECODE=1
 };
 
 class CDAE : public RecsysModelBase {
@@ -73,6 +74,7 @@ class CDAE : public RecsysModelBase {
     penalty_ = Penalty::create(mcfg.pt);
     if (const char* e = std::getenv("CDAE_B200_BATCH_USERS")) mcfg_.batch_users = std::strtoull(e, nullptr, 10);
     if (const char* e = std::getenv("CDAE_B200_DEVICE")) mcfg_.device = std::atoi(e);
+    if (const char* e = std::getenv("CDAE_B200_FULL_DECODE")) mcfg_.full_decode = std::atoi(e) != 0;
     LOG(INFO) << "CDAE (cdae_b200, ABI " << cdae_abi_version() << ") Configure: \n"
         << "\t{lambda: " << mcfg_.lambda << "}, "
         << "{Loss: " << loss_->loss_type() << "}, "
@@ -90,7 +92,8 @@ class CDAE : public RecsysModelBase {
         << "\t{Beta: " << mcfg_.beta << "}, "
         << "{LinearFunction: " << mcfg_.linear_function << "}, "
         << "{tanh: " << mcfg_.tanh << "}, "
-        << "{BatchUsers: " << mcfg_.batch_users << "}";
+        << "{BatchUsers: " << mcfg_.batch_users << "}, "
+        << "{FullDecode: " << mcfg_.full_decode << "}";
   }
 
   CDAE() : CDAE(CDAEConfig()) {}
@@ -142,6 +145,7 @@ class CDAE : public RecsysModelBase {
     c.linear_function = mcfg_.linear_function; c.tanh_act = mcfg_.tanh;
     c.batch_users = (int32_t)mcfg_.batch_users;
     c.device = mcfg_.device < 0 ? 0 : mcfg_.device;
+    c.full_decode = mcfg_.full_decode ? 1 : 0;
     cdae_handle* h = nullptr;
     check(cdae_create(&c, (int64_t)num_users_, (int64_t)num_items_, row_ptr.data(), col.data(), &h));
     st_ = std::make_shared<State>();
