@@ -518,8 +518,8 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   if (cfg->full_decode) {
     if (cfg->loss_type != CDAE_LOSS_CROSS_ENTROPY && cfg->loss_type != CDAE_LOSS_SQUARE)
       return set_error(CDAE_E_INVALID, "full_decode needs CROSS_ENTROPY or SQUARE loss");
-    if (cfg->num_dim + 2 > fd::MAX_KB * tc::KBLK)
-      return set_error(CDAE_E_INVALID, "full_decode needs num_dim <= %d", fd::MAX_KB * tc::KBLK - 2);
+    if (cfg->num_dim > fd::MAX_KB * tc::KBLK)
+      return set_error(CDAE_E_INVALID, "full_decode needs num_dim <= %d", fd::MAX_KB * tc::KBLK);
   }
   TRY(validate_csr(U, I, row_ptr, col));
   int ndev = 0;
@@ -627,7 +627,7 @@ int cdae_destroy(cdae_handle* h) {
   h->test_rp_d.release(); h->test_col_d.release();
   h->tc_zb.release(); h->tc_wb.release(); h->tc_wmax.release(); h->tc_eps.release();
   h->tc_thr.release(); h->tc_redo.release(); h->tc_redo_thr.release();
-  h->fd_zb.release(); h->fd_wb.release(); h->fd_g.release(); h->fd_bits.release();
+  h->fd_zb.release(); h->fd_wb.release(); h->fd_g.release(); h->fd_bits.release(); h->fd_bias.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);
   if (h->ev0) cudaEventDestroy(h->ev0);

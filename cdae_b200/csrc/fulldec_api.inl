@@ -25,27 +25,27 @@ static int fd_pick_split(int tiles, int units, int min_units, int sms, int max_s
   return 1;
 }
 
-template <int KB, int LT>
+template <int KB, int LT, bool BOUT>
 static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mg,
                            const fd::ScoreArgs& a, dim3 grid) {
   static bool attr_set = false;
   const size_t dyn = fd::score_smem(KB);
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT, BOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  fd::fd_score_kernel<KB, LT><<<grid, 640, dyn, h->stream>>>(ma, mb, mg, a);
+  fd::fd_score_kernel<KB, LT, BOUT><<<grid, 640, dyn, h->stream>>>(ma, mb, mg, a);
   return 0;
 }
-template <int KB, bool ITEMGRAD>
+template <int KB, bool ITEMGRAD, bool BOUT>
 static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const fd::GemmArgs& a, dim3 grid) {
   static bool attr_set = false;
   const size_t dyn = fd::gemm_smem(KB);
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  fd::fd_gemm_kernel<KB, ITEMGRAD><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
+  fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
   return 0;
 }
 template <int KB, int LT>
@@ -68,11 +68,15 @@ static int fd_launch_fused(cdae_handle* h, const CUtensorMap& ma, const CUtensor
     default: TRY(CALL(4)); break;      \
   }
 
+static bool K_has_bias_room(int K) { return K + 2 <= (int)round_up(K, tc::KBLK); }
+
 // H5-H7 with the output set = all items: fills bt.HG and adds the decoder-side
 // gradients of this rank's users to gW' / gb'.  bt.Z must hold the hidden activations.
 static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   if (bt.n_users == 0) return 0;
-  const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
+  // the output bias rides in the contraction (two spare columns) unless K leaves no room for them
+  const bool bias_in = K_has_bias_room(h->K);
+  const int K = h->K, Kp = (int)round_up(bias_in ? K + 2 : K, tc::KBLK), KB = Kp / tc::KBLK;
   const int64_t B_pad = round_up(bt.n_users, 128), I_pad = round_up(h->I, tc::TILE_I);
   TRY(ensure(h, h->fd_zb, (size_t)(B_pad * Kp)));
   TRY(ensure(h, h->fd_wb, (size_t)(I_pad * Kp)));
@@ -86,12 +90,17 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(h->fd_g.p);
   {
     ProfScope ps(h, CDAE_K_FD_PACK);
-    tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, wb);
+    if (bias_in) {
+      tc::pack_w_bf16_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, wb);
+    } else {
+      TRY(ensure(h, h->fd_bias, (size_t)I_pad));
+      fd::pack_w_plain_kernel<<<cdiv(I_pad * (Kp / 8), 256), 256, 0, h->stream>>>(Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, wb, h->fd_bias.p);
+    }
     KERNEL_OK(h);
     CU(cudaMemsetAsync(h->fd_bits.p, 0, sizeof(uint32_t) * (size_t)(B_pad * words), h->stream));
     fd::fd_bitmap_kernel<<<cdiv((int64_t)bt.n_users * 32, 256), 256, 0, h->stream>>>(bt.uids, bt.n_users, bt.row_ptr, bt.col, words, h->fd_bits.p);
     KERNEL_OK(h);
-    fd::pack_z_train_kernel<<<cdiv(B_pad * (Kp / 8), 256), 256, 0, h->stream>>>(bt.Z, bt.n_users, B_pad, K, h->ld, Kp, zb);
+    fd::pack_z_train_kernel<<<cdiv(B_pad * (Kp / 8), 256), 256, 0, h->stream>>>(bt.Z, bt.n_users, B_pad, K, h->ld, Kp, bias_in ? 1 : 0, zb);
     KERNEL_OK(h);
   }
   alignas(64) CUtensorMap m_zb_a, m_wb_b, m_g_st, m_g_rows, m_g_cols, m_wb_mn, m_zb_mn;
@@ -109,7 +118,7 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   // latency under the ~42 B/clk/SM the L2 can deliver when every SM streams W': profiles/r01_m_*),
   // so the split path is the default.
   static const bool fused_path = getenv("CDAE_B200_FD") && strcmp(getenv("CDAE_B200_FD"), "fused") == 0;
-  if (fused_path) {
+  if (fused_path && bias_in) {
     fd::FusedArgs a;
     a.n_users = bt.n_users; a.I = h->I; a.I_pad = I_pad; a.n_tiles = (int)(I_pad / fd::FU_TILE_I);
     a.ksteps = (K + 2 + 15) / 16; a.K = K; a.ld = h->ld;
@@ -133,19 +142,28 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   {
     fd::ScoreArgs a;
     a.n_users = bt.n_users; a.I = h->I; a.I_pad = I_pad; a.n_tiles = (int)(I_pad / tc::TILE_I);
-    a.ksteps = (K + 2 + 15) / 16;
+    a.ksteps = ((bias_in ? K + 2 : K) + 15) / 16;
     a.bits = h->fd_bits.p; a.G = G;
+    a.bias = bias_in ? nullptr : h->fd_bias.p;
     a.outputs = &h->stats_d->outputs[0];
     const int S = fd_pick_split(u_tiles, a.n_tiles, 4, h->sm_count, 32);
     a.tiles_per_split = (a.n_tiles + S - 1) / S;
     const dim3 grid(u_tiles, (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
     ProfScope ps(h, CDAE_K_FD_SCORE);
-    if (h->m.loss == LOSS_CE) {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_CE>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+    if (h->m.loss == LOSS_CE && bias_in) {
+#define CALL(KBV) fd_launch_score<KBV, LOSS_CE, false>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    } else if (h->m.loss == LOSS_CE) {
+#define CALL(KBV) fd_launch_score<KBV, LOSS_CE, true>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    } else if (bias_in) {
+#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE, false>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     } else {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE, true>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     }
@@ -160,7 +178,7 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     a.out = bt.HG; a.out_bias = nullptr; a.W = nullptr; a.bp = nullptr; a.nlambda = 0.f;
     const dim3 grid(u_tiles, (a.n_steps + a.steps_per_split - 1) / a.steps_per_split);
     ProfScope ps(h, CDAE_K_FD_HIDDEN);
-#define CALL(KBV) fd_launch_gemm<KBV, false>(h, m_g_rows, m_wb_mn, a, grid)
+#define CALL(KBV) fd_launch_gemm<KBV, false, false>(h, m_g_rows, m_wb_mn, a, grid)
     FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     KERNEL_OK(h);
@@ -177,9 +195,15 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     a.nlambda = (float)bt.n_users * h->m.lambda;
     const dim3 grid(i_tiles, (a.n_steps + a.steps_per_split - 1) / a.steps_per_split);
     ProfScope ps(h, CDAE_K_FD_ITEMGRAD);
-#define CALL(KBV) fd_launch_gemm<KBV, true>(h, m_g_cols, m_zb_mn, a, grid)
-    FD_DISPATCH_KB(KB, CALL)
+    if (bias_in) {
+#define CALL(KBV) fd_launch_gemm<KBV, true, false>(h, m_g_cols, m_zb_mn, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
 #undef CALL
+    } else {
+#define CALL(KBV) fd_launch_gemm<KBV, true, true>(h, m_g_cols, m_zb_mn, a, grid)
+      FD_DISPATCH_KB(KB, CALL)
+#undef CALL
+    }
     KERNEL_OK(h);
   }
   return 0;

@@ -31,13 +31,13 @@ constexpr int SC_STG_BYTES = 32 * 128;                // score kernel: one warp'
 constexpr int GM_STAGE = 4;                           // gemm kernels: contraction steps in flight
 constexpr int GM_A_BYTES = 128 * KBLK * 2;            // 16 KB: 128 (M) x 64 (kdim), either major
 constexpr int GM_BOX_BYTES = 64 * KBLK * 2;           // 8 KB : one {64, 64} box
-constexpr int MAX_KB = 4;                             // K + 2 <= 256
+constexpr int MAX_KB = 4;                             // Kp <= 256: K <= 256 (bias outside the contraction when K + 2 > Kp)
 
 __host__ __device__ constexpr size_t score_smem(int kb) {
   return 1024 + (size_t)kb * A_BLK_BYTES + (size_t)SC_STAGE * B_BLK_BYTES + 16 * SC_STG_BYTES + 256;
 }
 __host__ __device__ constexpr size_t gemm_smem(int kb) {
-  return 1024 + (size_t)GM_STAGE * (GM_A_BYTES + (size_t)kb * GM_BOX_BYTES) + 256;
+  return 1024 + (size_t)GM_STAGE * (GM_A_BYTES + (size_t)kb * GM_BOX_BYTES) + GM_BOX_BYTES /*ones slab*/ + 256;
 }
 __host__ __device__ constexpr int tmem_cols(int kb) { return kb == 1 ? 64 : kb == 2 ? 128 : 256; }
 
@@ -58,8 +58,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_major(int M, int N, int a
 // ---------------------------------------------------------------------------------------
 // Zb[r][0..K) = bf16(Z[r]), Zb[r][K] = Zb[r][K+1] = 1, rest 0; rows >= n are 0.  Z is the
 // minibatch-local hidden matrix [n][ld].  One thread per 8 columns.
+// bias_cols = 0: no bias / ones columns (K is a multiple of 64 or one short of it, e.g. config E's
+// K = 256: the bias is then added in the score epilogue and its gradient comes from a separate
+// ones-operand MMA in the item-gradient kernel).
 __global__ void __launch_bounds__(256) pack_z_train_kernel(const float* __restrict__ Z, int n, int64_t n_pad, int K,
-                                                           int ld, int Kp, __nv_bfloat16* __restrict__ out) {
+                                                           int ld, int Kp, int bias_cols,
+                                                           __nv_bfloat16* __restrict__ out) {
   const int g8 = Kp / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pad * g8) return;
@@ -70,10 +74,30 @@ __global__ void __launch_bounds__(256) pack_z_train_kernel(const float* __restri
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
     float v = 0.f;
-    if (r < n) v = c < K ? Z[r * ld + c] : (c <= K + 1 ? 1.f : 0.f);
+    if (r < n) v = c < K ? Z[r * ld + c] : ((bias_cols && c <= K + 1) ? 1.f : 0.f);
     o[j] = __float2bfloat16_rn(v);
   }
   *reinterpret_cast<uint4*>(out + r * Kp + c0) = *reinterpret_cast<const uint4*>(o);
+}
+
+// Wb for the bias-outside mode: plain bf16 copy of W' (pad rows / columns 0) and b' zero-padded to
+// I_pad floats for the score epilogue.  One thread per 8 columns.
+__global__ void __launch_bounds__(256) pack_w_plain_kernel(const float* __restrict__ W, const float* __restrict__ bp,
+                                                           int64_t I, int64_t I_pad, int K, int ld, int Kp,
+                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ bias_pad) {
+  const int g8 = Kp / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I_pad * g8) return;
+  const int64_t r = idx / g8;
+  const int c0 = (int)(idx % g8) * 8;
+  __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    o[j] = __float2bfloat16_rn((r < I && c < K) ? W[r * ld + c] : 0.f);
+  }
+  *reinterpret_cast<uint4*>(out + r * Kp + c0) = *reinterpret_cast<const uint4*>(o);
+  if (c0 == 0) bias_pad[r] = r < I ? bp[r] : 0.f;
 }
 
 // Target bitmap of a minibatch slice: bit i of row r <=> item i is in the train row of user uids[r]
@@ -152,6 +176,7 @@ struct ScoreArgs {
   int tiles_per_split;       // gridDim.y CTAs share the item tiles of one user tile
   int ksteps;                // ceil((K + 2) / 16): MMA k-steps that hold non-zero operands
   const uint32_t* bits;      // [B_pad][I_pad / 32] target bitmap of the slice (fd_bitmap_kernel)
+  const float* bias;         // [I_pad] b' zero-padded, bias-outside mode only (BOUT)
   __nv_bfloat16* G;          // [B_pad][I_pad] loss gradients dl/dy, 0 in pad rows / pad columns
   unsigned long long* outputs;  // stats: scored outputs
 };
@@ -159,12 +184,17 @@ struct ScoreArgs {
 // One 32-column chunk: y -> g = l'(y, t) -> bf16 -> 64 bytes of this thread's row of the warp's
 // staging tile ([32 rows][128 bytes], 128-byte swizzled like every TMA tile: 16-byte piece c of
 // row r lives at piece c ^ (r & 7)); cbase = 0 / 4 selects the half of the row.
-template <int LT>
+template <int LT, bool BOUT = false>
 __device__ __forceinline__ void grad_compute(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
-                                             uint32_t (&o)[16]) {
+                                             uint32_t (&o)[16], const float* bias = nullptr) {
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
-    const float y0 = __uint_as_float(v[j]), y1 = __uint_as_float(v[j + 1]);
+    float y0 = __uint_as_float(v[j]), y1 = __uint_as_float(v[j + 1]);
+    if (BOUT) {                      // b' outside the contraction: the same 8 bytes for every lane (L1 broadcast)
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + j));
+      y0 += b.x;
+      y1 += b.y;
+    }
     // target as a float without a conversion: bit j of pos -> 0x3f800000 (1.0f) or 0
     const float t0 = __uint_as_float(((pos >> j) & 1u) * 0x3f800000u);
     const float t1 = __uint_as_float(((pos >> (j + 1)) & 1u) * 0x3f800000u);
@@ -196,11 +226,11 @@ __device__ __forceinline__ void grad_store(const uint32_t (&o)[16], unsigned cha
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(srow + (((cbase + j) ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
-template <int LT>
+template <int LT, bool BOUT = false>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos, uint32_t valid, bool row_ok,
-                                           unsigned char* srow, int cbase, int sw) {
+                                           unsigned char* srow, int cbase, int sw, const float* bias = nullptr) {
   uint32_t o[16];
-  grad_compute<LT>(v, pos, valid, row_ok, o);
+  grad_compute<LT, BOUT>(v, pos, valid, row_ok, o, bias);
   grad_store(o, srow, cbase, sw);
 }
 
@@ -223,7 +253,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // beforehand (fd_bitmap_kernel): walking the CSR rows inside this kernel, as the recommend kernel
 // does, serialises one dependent global load per positive and made two helper warps the pace of
 // the whole kernel at config C's 145 items per user (profiles/r01_j_*).
-template <int KB, int LT>
+template <int KB, int LT, bool BOUT>
 __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b,
                                                           const __grid_constant__ CUtensorMap map_g, ScoreArgs a) {
@@ -341,7 +371,7 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
       tmem_ld_wait(v);
       {
         const uint32_t valid = item0 + 32 <= a.I ? 0xffffffffu : (item0 >= a.I ? 0u : ((1u << (int)(a.I - item0)) - 1u));
-        grad_chunk<LT>(v, cb.x, valid, row_ok, srow, 0, sw);
+        grad_chunk<LT, BOUT>(v, cb.x, valid, row_ok, srow, 0, sw, a.bias + item0);
       }
       tmem_ld32_issue(col0 + 32u, v);
       tmem_ld_wait(v);
@@ -351,7 +381,7 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
       {
         const int64_t first = item0 + 32;
         const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
-        grad_chunk<LT>(v, cb.y, valid, row_ok, srow, 4, sw);
+        grad_chunk<LT, BOUT>(v, cb.y, valid, row_ok, srow, 4, sw, a.bias + first);
       }
       fence_proxy_async();                         // staging writes -> visible to the TMA engine
       __syncwarp();
@@ -628,18 +658,27 @@ struct GemmArgs {
 // One CTA = one 128-row output tile x all Kp columns (accumulator: Kp TMEM columns), walking its
 // share of the contraction in steps of 64 through a GM_STAGE-deep TMA ring.
 // warp 0 TMA · warp 1 MMA issue · warp 2 TMEM owner · warps 4-7 epilogue (thread = output row).
-template <int KB, bool ITEMGRAD>
+template <int KB, bool ITEMGRAD, bool BOUT = false>
 __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b, GemmArgs a) {
   constexpr int STAGE_BYTES = GM_A_BYTES + KB * GM_BOX_BYTES;
   constexpr int NCOL = KB * KBLK;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGE * STAGE_BYTES);
+  // bias-outside mode: gb' = G^T 1 comes from a second, 16-column accumulator fed by a constant
+  // all-ones MN-major slab (64 contraction rows x 128 bytes)
+  unsigned char* sOnes = smem + GM_STAGE * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (BOUT ? GM_BOX_BYTES : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + GM_STAGE;
   uint64_t* t_full = bars + 2 * GM_STAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+  constexpr int TCOLS = BOUT ? 512 : tmem_cols(KB);
+  constexpr uint32_t ONES_COL = 256;
+  if (BOUT) {
+    for (int i = threadIdx.x; i < GM_BOX_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3f803f80u;
+    fence_proxy_async();
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -658,7 +697,7 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
     mbar_init(t_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols(KB));
+  if (warp == 2) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -701,6 +740,10 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
           const uint64_t ad = ITEMGRAD ? umma_desc_mn_sw128(a0 + k * 2048, GM_BOX_BYTES) : umma_desc_sw128(a0 + k * 32);
           const uint64_t bd = umma_desc_mn_sw128(b0 + k * 2048, GM_BOX_BYTES);
           umma_bf16(tmem_base, ad, bd, idesc, (t | k) != 0);
+          if (BOUT) {
+            constexpr uint32_t idesc1 = umma_idesc_bf16_major(128, 16, 1, 1);
+            umma_bf16(tmem_base + ONES_COL, ad, umma_desc_mn_sw128(smem_u32(sOnes) + k * 2048, GM_BOX_BYTES), idesc1, (t | k) != 0);
+          }
         }
         umma_commit(empty + s);
         if (++s == GM_STAGE) { s = 0; ph ^= 1; }
@@ -714,7 +757,17 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     mbar_wait(t_full, 0);
     tc_fence_after();
-    const int last_col = ITEMGRAD ? a.K : a.K - 1;     // column K of the item gradient is gb'
+    const int last_col = (ITEMGRAD && !BOUT) ? a.K : a.K - 1;     // column K of the item gradient is gb'
+    if (BOUT) {
+      uint32_t v1[32];
+      tmem_ld32_issue(lane_addr + ONES_COL, v1);   // 16 identical columns (+ 16 unused ones)
+      tmem_ld_wait(v1);
+      if (row_ok) {
+        float gb = __uint_as_float(v1[0]);
+        if (blockIdx.y == 0 && a.nlambda != 0.f) gb = fmaf(a.nlambda, a.bp[row], gb);
+        red_add_f32(a.out_bias + row, gb);
+      }
+    }
     const bool add_l2 = ITEMGRAD && blockIdx.y == 0 && a.nlambda != 0.f;
     for (int c = 0; c * 32 <= last_col; ++c) {
       uint32_t v[32];
@@ -726,7 +779,7 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
         const int col = c * 32 + j;
         if (col > last_col) break;
         float x[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
-        if (ITEMGRAD && col <= a.K && col + 3 >= a.K) {
+        if (ITEMGRAD && !BOUT && col <= a.K && col + 3 >= a.K) {
           const int kk = a.K - col;
           float gb = kk == 0 ? x[0] : kk == 1 ? x[1] : kk == 2 ? x[2] : x[3];
           if (add_l2) gb = fmaf(a.nlambda, a.bp[row], gb);
@@ -751,7 +804,7 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols(KB));
+    tmem_dealloc(tmem_base, TCOLS);
   }
 }
 

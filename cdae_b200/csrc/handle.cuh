@@ -97,6 +97,7 @@ struct cdae_handle {
   // full-item-decode training (fulldec_tc.cuh): bf16 operands and the loss-gradient matrix
   cdae::DevBuf<uint16_t> fd_zb, fd_wb, fd_g;   // [B_pad][Kp], [I_pad][Kp], [B_pad][I_pad]
   cdae::DevBuf<uint32_t> fd_bits;              // [B_pad][I_pad / 32] target bitmap of the slice
+  cdae::DevBuf<float> fd_bias;                 // [I_pad] b' zero-padded (bias-outside mode, K + 2 > Kp)
   cdae::DevBuf<int64_t> test_rp_d;
   cdae::DevBuf<int32_t> test_col_d;
   std::vector<int32_t> topn_ids_h;    // host mirror for thread-safe lookups

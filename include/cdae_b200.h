@@ -87,7 +87,7 @@ typedef struct cdae_config {
                                  on the train row, 0 elsewhere) instead of positives + num_neg
                                  sampled negatives; the K x I contraction runs on tcgen05/TMEM with
                                  bf16 operands (no reference function: SURVEY.md H12).  Needs
-                                 CROSS_ENTROPY or SQUARE loss and num_dim <= 254; batch_users 0 ->
+                                 CROSS_ENTROPY or SQUARE loss and num_dim <= 256; batch_users 0 ->
                                  128 x SM count. */
   int32_t reserved[6];
 } cdae_config_t;

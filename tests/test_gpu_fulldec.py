@@ -28,6 +28,11 @@ CASES = [
     # near 1e-4 a step is lr*g/sqrt(acc), which amplifies a single bf16 rounding flip of one z
     # element (fp32 vs fp64 hidden value on either side of a bf16 boundary) by up to 10x
     (140, 600, 62, dict(loss="CE", asymmetric=True, linear_function=True, tanh=True, beta=1.0)),
+    # no room for the two bias columns (K + 2 > round_up(K, 64)): b' is added in the score epilogue and
+    # its gradient comes from the ones-operand MMA of the item-gradient kernel
+    (200, 800, 256, dict(loss="CE", asymmetric=True, beta=1.0)),                    # config E's K
+    (130, 500, 64, dict(loss="SQUARE", beta=1.0, learn_rate=0.01)),                 # tied
+    (150, 640, 63, dict(loss="CE", asymmetric=True, beta=1.0)),
 ]
 
 
