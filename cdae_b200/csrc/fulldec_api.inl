@@ -26,15 +26,26 @@ static int fd_pick_split(int tiles, int units, int min_units, int sms, int max_s
 }
 
 template <int KB, int LT, bool BOUT>
-static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mg,
-                           const fd::ScoreArgs& a, dim3 grid) {
+static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb_half,
+                           const CUtensorMap& mg, const fd::ScoreArgs& a, dim3 grid, bool cluster2) {
   static bool attr_set = false;
   const size_t dyn = fd::score_smem(KB);
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT, BOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT, BOUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT, BOUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  fd::fd_score_kernel<KB, LT, BOUT><<<grid, 640, dyn, h->stream>>>(ma, mb, mg, a);
+  if (!cluster2) {
+    fd::fd_score_kernel<KB, LT, BOUT, false><<<grid, 640, dyn, h->stream>>>(ma, mb, mg, a);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = dyn; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, fd::fd_score_kernel<KB, LT, BOUT, true>, ma, mb_half, mg, a));
   return 0;
 }
 template <int KB, bool ITEMGRAD, bool BOUT>
@@ -49,15 +60,26 @@ static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorM
   return 0;
 }
 template <int KB, int LT>
-static int fd_launch_fused(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mg,
-                           const fd::FusedArgs& a, dim3 grid) {
+static int fd_launch_fused(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw_half,
+                           const CUtensorMap& mg, const fd::FusedArgs& a, dim3 grid, bool cluster2) {
   static bool attr_set = false;
   const size_t dyn = fd::fused_smem(KB);
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(fd::fd_fused_kernel<KB, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_fused_kernel<KB, LT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_fused_kernel<KB, LT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  fd::fd_fused_kernel<KB, LT><<<grid, 640, dyn, h->stream>>>(ma, mw, mg, a);
+  if (!cluster2) {
+    fd::fd_fused_kernel<KB, LT, false><<<grid, 640, dyn, h->stream>>>(ma, mw, mg, a);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = dyn; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, fd::fd_fused_kernel<KB, LT, true>, ma, mw_half, mg, a));
   return 0;
 }
 #define FD_DISPATCH_KB(KBV, CALL)      \
@@ -113,10 +135,11 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   TRY(tc_make_map(&m_zb_mn, zb, (uint64_t)B_pad, (uint64_t)Kp, 64));           // itemgrad: B = Zb, {64 cols, 64 users}
   const int u_tiles = (int)(B_pad / 128);
   // CDAE_B200_FD=fused: score + hidden-gradient contraction in ONE kernel (fd_fused_kernel).  Parity-
-  // identical; measured 9 % slower than the two launches at config C (its W' tiles stay in shared
-  // memory from the first contraction to the second, which leaves too few slots to hide the TMA
-  // latency under the ~42 B/clk/SM the L2 can deliver when every SM streams W': profiles/r01_m_*),
-  // so the split path is the default.
+  // identical; measured 9 % slower than the two launches at config C: its epilogue warps wait for
+  // scores 70 % of the time (profiles/r01_m_*).  Halving the W' stream with 2-CTA multicast
+  // (CDAE_B200_FD_CLUSTER, on by default for this kernel) did not change that, so the stall is in
+  // the hand-off chain (TMA latency of whole-tile slots / single MMA-issue thread), not in L2
+  // bandwidth.  The split path is the default.
   static const bool fused_path = getenv("CDAE_B200_FD") && strcmp(getenv("CDAE_B200_FD"), "fused") == 0;
   if (fused_path && bias_in) {
     fd::FusedArgs a;
@@ -127,13 +150,17 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     const int S = fd_pick_split(u_tiles, a.n_tiles, 16, h->sm_count, 32);
     a.tiles_per_split = (a.n_tiles + S - 1) / S;
     const dim3 grid(u_tiles, (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    static const bool cl_off = getenv("CDAE_B200_FD_CLUSTER") && atoi(getenv("CDAE_B200_FD_CLUSTER")) == 0;
+    const bool cluster2 = !cl_off && (u_tiles % 2 == 0);
+    alignas(64) CUtensorMap m_wb_q;
+    TRY(tc_make_map(&m_wb_q, wb, (uint64_t)I_pad, (uint64_t)Kp, fd::FU_TILE_I / 2));
     ProfScope ps(h, CDAE_K_FD_SCORE);
     if (h->m.loss == LOSS_CE) {
-#define CALL(KBV) fd_launch_fused<KBV, LOSS_CE>(h, m_zb_a, m_wb_mn, m_g_rows, a, grid)
+#define CALL(KBV) fd_launch_fused<KBV, LOSS_CE>(h, m_zb_a, m_wb_mn, m_wb_q, m_g_rows, a, grid, cluster2)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     } else {
-#define CALL(KBV) fd_launch_fused<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_mn, m_g_rows, a, grid)
+#define CALL(KBV) fd_launch_fused<KBV, LOSS_SQUARE>(h, m_zb_a, m_wb_mn, m_wb_q, m_g_rows, a, grid, cluster2)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     }
@@ -149,21 +176,27 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
     const int S = fd_pick_split(u_tiles, a.n_tiles, 4, h->sm_count, 32);
     a.tiles_per_split = (a.n_tiles + S - 1) / S;
     const dim3 grid(u_tiles, (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+    // CDAE_B200_FD_CLUSTER=1: pairs of user tiles share their W' stream through 2-CTA clusters
+    // (parity-identical, measured neutral: see fd_score_kernel)
+    static const bool cl_on = getenv("CDAE_B200_FD_CLUSTER") && atoi(getenv("CDAE_B200_FD_CLUSTER")) != 0;
+    const bool cluster2 = cl_on && (u_tiles % 2 == 0);
+    alignas(64) CUtensorMap m_wb_half;
+    TRY(tc_make_map(&m_wb_half, wb, (uint64_t)I_pad, (uint64_t)Kp, tc::TILE_I / 2));
     ProfScope ps(h, CDAE_K_FD_SCORE);
     if (h->m.loss == LOSS_CE && bias_in) {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_CE, false>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_CE, false>(h, m_zb_a, m_wb_b, m_wb_half, m_g_st, a, grid, cluster2)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     } else if (h->m.loss == LOSS_CE) {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_CE, true>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_CE, true>(h, m_zb_a, m_wb_b, m_wb_half, m_g_st, a, grid, cluster2)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     } else if (bias_in) {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE, false>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE, false>(h, m_zb_a, m_wb_b, m_wb_half, m_g_st, a, grid, cluster2)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     } else {
-#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE, true>(h, m_zb_a, m_wb_b, m_g_st, a, grid)
+#define CALL(KBV) fd_launch_score<KBV, LOSS_SQUARE, true>(h, m_zb_a, m_wb_b, m_wb_half, m_g_st, a, grid, cluster2)
       FD_DISPATCH_KB(KB, CALL)
 #undef CALL
     }

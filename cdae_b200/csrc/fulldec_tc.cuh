@@ -160,6 +160,8 @@ __device__ __forceinline__ void sigmoid2(float y0, float y1, float& s0, float& s
   p = fma2(p, a, pack2(0.999991238117218f, 0.999991238117218f));
   float q0, q1;
   unpack2(mul2(p, a), q0, q1);          // sigma(-|y|) in (0, 0.5]
+  // (a comparison-free form, copysign(0.5 - q, y) + (0.5 - t), needs fewer issue slots but was not
+  // faster — the kernel is not issue-bound — and loses the relative precision of small sigma)
   s0 = y0 >= 0.f ? 1.f - q0 : q0;
   s1 = y1 >= 0.f ? 1.f - q1 : q1;
 }
@@ -239,6 +241,31 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 2-CTA cluster helpers: a TMA load whose bytes (and mbarrier completion) land at the same
+// shared-memory offsets of every CTA in ctaMask, and a tcgen05.commit that arrives on the same
+// barrier offset of every CTA in ctaMask.
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -253,7 +280,14 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // beforehand (fd_bitmap_kernel): walking the CSR rows inside this kernel, as the recommend kernel
 // does, serialises one dependent global load per positive and made two helper warps the pace of
 // the whole kernel at config C's 145 items per user (profiles/r01_j_*).
-template <int KB, int LT, bool BOUT>
+// CL2: launched as clusters of two CTAs (two user tiles, same item range).  Every W' k-block is
+// needed by both, so each CTA fetches HALF of it (128 of the 256 item rows) and multicasts it into
+// both shared memories: the L2 -> SM stream of W' (148 x |Wb| per launch, the kernel's largest L2
+// consumer) is cut in two.  A stage is released to the producers when BOTH tensor cores are done with it.
+// Measured neutral at config C (0.805 vs 0.799 ms per two launches: this kernel is not bound by
+// that stream), so it is opt-in (CDAE_B200_FD_CLUSTER=1); kept as the building block the fused
+// kernel needs, where the W' slots ARE the limit.
+template <int KB, int LT, bool BOUT, bool CL2>
 __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_b,
                                                           const __grid_constant__ CUtensorMap map_g, ScoreArgs a) {
@@ -283,7 +317,7 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SC_STAGE; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
+      mbar_init(empty + s, CL2 ? 2 : 1);
     }
     mbar_init(a_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -299,6 +333,8 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
+  if (CL2) cluster_sync_all();            // the peer's barriers are initialised before anything is multicast
 
   if (warp == 0) {
     if (lane == 0 && n_t > 0) {
@@ -310,7 +346,11 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
           mbar_arrive_expect_tx(full + s, B_BLK_BYTES);
-          tma_load_2d(sB + s * B_BLK_BYTES, &map_b, full + s, kb * KBLK, (t_lo + t) * TILE_I);
+          if (CL2)   // map_b has 128-row boxes: my half of the k-block, into both CTAs
+            tma_load_2d_mc(sB + s * B_BLK_BYTES + crank * (B_BLK_BYTES / 2), &map_b, full + s, kb * KBLK,
+                           (t_lo + t) * TILE_I + (int)crank * (TILE_I / 2), (uint16_t)0x3);
+          else
+            tma_load_2d(sB + s * B_BLK_BYTES, &map_b, full + s, kb * KBLK, (t_lo + t) * TILE_I);
           if (++s == SC_STAGE) { s = 0; ph ^= 1; }
         }
       }
@@ -333,7 +373,8 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
           const int nk = min(KBLK / 16, a.ksteps - kb * (KBLK / 16));   // trailing k-steps are all zero
           for (int k = 0; k < nk; ++k)
             umma_bf16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
-          umma_commit(empty + s);
+          if (CL2) umma_commit_mc(empty + s, (uint16_t)0x3);
+          else umma_commit(empty + s);
           if (++s == SC_STAGE) { s = 0; ph ^= 1; }
         }
         umma_commit(t_full + buf);
@@ -400,6 +441,7 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (CL2) cluster_sync_all();            // no CTA leaves while its peer may still multicast into it
 }
 
 // ---------------------------------------------------------------------------------------
@@ -440,7 +482,9 @@ struct FusedArgs {
   unsigned long long* outputs;
 };
 
-template <int KB, int LT>
+// CL2: clusters of two CTAs (two user tiles, same item range) fetch half of every W' tile each and
+// multicast it into both shared memories; a slot is refilled when both tensor cores released it.
+template <int KB, int LT, bool CL2>
 __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_w,
                                                           const __grid_constant__ CUtensorMap map_g, FusedArgs a) {
@@ -477,7 +521,7 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < FU_SLOTS; ++i) {
       mbar_init(w_full + i, 1);
-      mbar_init(w_empty + i, 1);
+      mbar_init(w_empty + i, CL2 ? 2 : 1);
     }
     mbar_init(a_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -497,6 +541,8 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
+  if (CL2) cluster_sync_all();
 
   if (warp == 0) {
     if (lane == 0 && n_t > 0) {
@@ -506,8 +552,14 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
         const int slot = t % FU_SLOTS;
         mbar_wait(w_empty + slot, ((t / FU_SLOTS) & 1) ^ 1);
         mbar_arrive_expect_tx(w_full + slot, W_TILE_BYTES);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sW + slot * W_TILE_BYTES + kb * GM_BOX_BYTES, &map_w, w_full + slot, kb * KBLK, (t_lo + t) * FU_TILE_I);
+        for (int kb = 0; kb < KB; ++kb) {
+          unsigned char* dst = sW + slot * W_TILE_BYTES + kb * GM_BOX_BYTES;
+          if (CL2)   // map_w has 32-row boxes: my half of the rows, into both CTAs
+            tma_load_2d_mc(dst + crank * (GM_BOX_BYTES / 2), &map_w, w_full + slot, kb * KBLK,
+                           (t_lo + t) * FU_TILE_I + (int)crank * (FU_TILE_I / 2), (uint16_t)0x3);
+          else
+            tma_load_2d(dst, &map_w, w_full + slot, kb * KBLK, (t_lo + t) * FU_TILE_I);
+        }
       }
     }
   } else if (warp == 1) {
@@ -547,7 +599,8 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
           umma_bf16(tmem_base + HG_COL, umma_desc_sw128(g0 + k * 32), umma_desc_mn_sw128(w0 + k * 2048, GM_BOX_BYTES),
                     idesc2, (t | k) != 0);
         umma_commit(g_empty + sb);
-        umma_commit(w_empty + slot);
+        if (CL2) umma_commit_mc(w_empty + slot, (uint16_t)0x3);
+        else umma_commit(w_empty + slot);
       }
       umma_commit(hg_full);
     }
@@ -637,6 +690,7 @@ __global__ void __launch_bounds__(640, 1) fd_fused_kernel(const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (CL2) cluster_sync_all();
 }
 
 // ---------------------------------------------------------------------------------------
