@@ -135,11 +135,12 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   TRY(tc_make_map(&m_zb_mn, zb, (uint64_t)B_pad, (uint64_t)Kp, 64));           // itemgrad: B = Zb, {64 cols, 64 users}
   const int u_tiles = (int)(B_pad / 128);
   // CDAE_B200_FD=fused: score + hidden-gradient contraction in ONE kernel (fd_fused_kernel).  Parity-
-  // identical; measured 9 % slower than the two launches at config C: its epilogue warps wait for
-  // scores 70 % of the time (profiles/r01_m_*).  Halving the W' stream with 2-CTA multicast
-  // (CDAE_B200_FD_CLUSTER, on by default for this kernel) did not change that, so the stall is in
-  // the hand-off chain (TMA latency of whole-tile slots / single MMA-issue thread), not in L2
-  // bandwidth.  The split path is the default.
+  // identical; measured 9 % slower than the two launches at config C (profiles/r01_m_*).  What was
+  // tried: 2-CTA multicast of the W' tiles (halves the L2 stream: no change), a second W' ring so
+  // that no slot is held across the epilogue (+32 KB of shared-memory writes per tile: 12 % SLOWER).
+  // Both say the kernel is bound by shared-memory bandwidth: with 64-item tiles every N = 64 MMA
+  // re-reads its 4 KB A slice for 2 KB of B, and the second contraction adds 12 KB per k-step.
+  // The split path is the default.
   static const bool fused_path = getenv("CDAE_B200_FD") && strcmp(getenv("CDAE_B200_FD"), "fused") == 0;
   if (fused_path && bias_in) {
     fd::FusedArgs a;
