@@ -6,3 +6,4 @@ thin callers of the C ABI in include/cdae_b200.h, implemented by hand-written sm
 in cdae_b200/csrc/."""
 from ._lib import CdaeError  # noqa: F401
 from .model import CDAE, CDAEConfig  # noqa: F401
+from .data import Dataset  # noqa: F401

@@ -74,6 +74,15 @@ SIGNATURES = {
     "cdae_host_free": (C.c_int, [C.c_void_p]),
     "cdae_synchronize": (C.c_int, [C.c_void_p]),
     "cdae_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cdae_dataset_load_pairs": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cdae_dataset_info": (C.c_int, [C.c_void_p, i64p, i64p, i64p]),
+    "cdae_dataset_split": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64]),
+    "cdae_dataset_nnz": (C.c_int, [C.c_void_p, C.c_int32, i64p]),
+    "cdae_dataset_csr": (C.c_int, [C.c_void_p, C.c_int32, i64p, i32p]),
+    "cdae_dataset_raw_id": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_char_p)]),
+    "cdae_dataset_free": (C.c_int, [C.c_void_p]),
+    "cdae_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cdae_load": (C.c_int, [C.c_void_p, C.c_char_p]),
 }
 
 KERNEL_CLASSES = ["sample", "gather", "activate", "decode", "hidden_bwd", "scatter", "allreduce",

@@ -1026,3 +1026,4 @@ static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users
 
 #include "topn_api.inl"
 #include "fulldec_api.inl"
+#include "dataset.inl"

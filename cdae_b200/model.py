@@ -269,6 +269,14 @@ class CDAE:
         buf = C.create_string_buffer(unique_id, 128)
         _lib.check(self._L.cdae_dist_init(self._h, rank, world, buf))
 
+    def save(self, path):
+        """Versioned binary checkpoint of every parameter block incl. AdaGrad state (cdae_save)."""
+        _lib.check(self._L.cdae_save(self._h, str(path).encode()))
+
+    def load(self, path):
+        _lib.check(self._L.cdae_load(self._h, str(path).encode()))
+        self._topk = 0
+
     def profile(self, enable=True):
         _lib.check(self._L.cdae_profile(self._h, int(enable)))
 

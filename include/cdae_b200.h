@@ -183,6 +183,36 @@ int cdae_topn_fetch(cdae_handle* h, int64_t* ids_out, float* scores_out);
 int cdae_topn_evaluate(cdae_handle* h, const int64_t* test_row_ptr, const int32_t* test_col,
                        double* out8, int64_t* users_evaluated);
 
+/* ---- the data path in front of the hot path (host only) ----
+ * Data::load(file, RECSYS, parser, skip_header) (data-inl.hpp:45-64) for "user<delim>item" lines as
+ * apps/yelp parses them (yelp.cpp:60-66; split_line drops empty tokens, file_utils.hpp:15-25; empty
+ * lines are skipped and not counted, file_line_reader-inl.hpp:12-19), with the reference's id
+ * assignment — dense ids in FIRST-SEEN order per column (FeatureGroupInfo::get_index,
+ * instance-inl.hpp:22-37) — straight into the CSR cdae_create() takes (rows ascending, duplicate
+ * pairs collapsed like the hash of hashes of recsys_model_base.hpp:29-34 does).  A line that does
+ * not have exactly two fields is CDAE_E_INVALID (the reference CHECK-aborts, yelp.cpp:62). */
+typedef struct cdae_dataset cdae_dataset;
+int cdae_dataset_load_pairs(const char* path, const char* delimiters /* NULL -> " " */,
+                            int32_t skip_header, cdae_dataset** out);
+int cdae_dataset_info(const cdae_dataset* d, int64_t* users, int64_t* items, int64_t* instances);
+/* Data::random_split_by_feature_group(train, test, 0, test_ratio) (data-inl.hpp:231-272): per user,
+ * a uniformly random floor(n_u * test_ratio) of its instances go to test.  Philox stream keyed by
+ * (seed, user) instead of the reference's time-seeded mt19937_64. */
+int cdae_dataset_split(cdae_dataset* d, double test_ratio, uint64_t seed);
+/* which: 0 = all pairs, 1 = train, 2 = test (1, 2 need cdae_dataset_split).  row_ptr: users + 1. */
+int cdae_dataset_nnz(const cdae_dataset* d, int32_t which, int64_t* nnz);
+int cdae_dataset_csr(const cdae_dataset* d, int32_t which, int64_t* row_ptr, int32_t* col_idx);
+/* the raw string of a dense id (group 0 = users, 1 = items): FeatureGroupInfo::raw_str_map_ */
+int cdae_dataset_raw_id(const cdae_dataset* d, int32_t group, int64_t idx, const char** out);
+int cdae_dataset_free(cdae_dataset* d);
+
+/* Model checkpoint (the reference has none — its save/load only cover Data):
+ * versioned binary file with the config, the shape and every parameter block incl. AdaGrad state
+ * as doubles.  cdae_load needs a handle created with the same shape and the same structural
+ * options (asymmetric, user_factor, linear_function).  Single-process. */
+int cdae_save(cdae_handle* h, const char* path);
+int cdae_load(cdae_handle* h, const char* path);
+
 /* Data parallelism over the GPUs of one node: one process per GPU, each owning the user
  * shard [rank*U/world, (rank+1)*U/world) of every minibatch; item-side parameters are
  * replicated and kept identical by all-reducing the dense gradients.  nccl_unique_id is

@@ -290,3 +290,26 @@ def test_errors_are_reported_not_swallowed(orc):
     m.init_params(1)
     with pytest.raises(CdaeError):
         m.train_one_iteration(seed=1, epoch=0)
+
+
+def test_checkpoint_round_trip(orc, tmp_path):
+    """cdae_save / cdae_load: every block incl. AdaGrad state survives, a model restored
+    into a fresh handle scores and recommends identically, and mismatching shapes are refused."""
+    from cdae_b200 import CdaeError
+    from cdae_b200._lib import PARAMS
+    cfg = orc.default_config(loss="CE", num_dim=20, beta=1.0, asymmetric=True, linear_function=True)
+    data = cases.small_dataset(U=90, I=300, mean=10.0, seed=4)
+    U, I, rp, col = data["U"], data["I"], data["train_row_ptr"], data["train_col"]
+    m = gpu_model(cfg, U, I, rp, col, cases.random_params(U, I, 20, 2, True, True, True))
+    m.train_one_iteration(seed=3, epoch=0)
+    path = tmp_path / "model.ckpt"
+    m.save(path)
+    m2 = gpu_model(cfg, U, I, rp, col, {})
+    m2.load(path)
+    for k in PARAMS:
+        np.testing.assert_array_equal(m.get_param(k), m2.get_param(k), err_msg=k)
+    assert m.recommend_all(10)[0].tolist() == m2.recommend_all(10)[0].tolist()
+    m3 = gpu_model(orc.default_config(loss="CE", num_dim=21, beta=1.0, asymmetric=True, linear_function=True),
+                   U, I, rp, col, {})
+    with pytest.raises(CdaeError):
+        m3.load(path)
