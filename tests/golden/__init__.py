@@ -4,7 +4,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NAMES = sorted(f[:-4] for f in os.listdir(HERE) if f.endswith(".npz"))
+NAMES = sorted(f[:-4] for f in os.listdir(HERE) if f.endswith(".npz") and not f.startswith("pairs_"))   # pairs_*: loader fixtures
 
 
 def load(name):
