@@ -92,6 +92,24 @@ static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_
   a.users = users; a.row_ptr = h->row_ptr_d.p; a.col = h->col_d.p;
   a.cand_id = h->cand_id.p; a.cand_s = h->cand_s.p; a.cand_cnt = h->cand_cnt.p; a.cand_thr = h->tc_thr.p;
   a.init_thr = init_thr;
+  // Dense rows (more than ~half a rated item per user per 256-item tile, e.g. config C's 145 items over
+  // 106 tiles): walking the CSR inside the kernel is one dependent global load per item and paces the
+  // whole kernel (profiles/r01_h_*: 139 TFLOP/s at config C against 965 at config D), so the rated sets
+  // become a bitmap first.  Sparse rows keep the in-kernel walk (the bitmap would cost more than it saves).
+  a.bits = nullptr;
+  a.words = I_pad / 32;
+  const double per_tile = (double)h->nnz / (double)std::max<int64_t>(h->U, 1) / (double)(I_pad / tc::TILE_I);
+  static const char* bm_env = getenv("CDAE_B200_TOPN_BITMAP");      // "0" / "1" force the choice (A/B runs)
+  const bool want_bits = bm_env ? atoi(bm_env) != 0 : per_tile > 0.5;
+  if (want_bits && (size_t)n_pad * (size_t)a.words * 4 <= ((size_t)8 << 30)) {
+    TRY(ensure(h, h->fd_bits, (size_t)(n_pad * a.words)));
+    CU(cudaMemsetAsync(h->fd_bits.p, 0, sizeof(uint32_t) * (size_t)(n_pad * a.words), h->stream));
+    ProfScope ps(h, CDAE_K_TOPN_PACK);
+    tc::topn_bitmap_kernel<<<cdiv(n_users * 32, 256), 256, 0, h->stream>>>(users, (int)n_users, h->row_ptr_d.p, h->col_d.p,
+                                                                          h->I, a.words, h->fd_bits.p);
+    KERNEL_OK(h);
+    a.bits = h->fd_bits.p;
+  }
   const int grid = (int)(n_pad / tc::TILE_U);
   // Item ranges: a sweep that starts from known thresholds (init_thr) is paced by the MMA, not by
   // candidate handling, and has few user tiles — cut the items into ranges while the grid still fits one wave.

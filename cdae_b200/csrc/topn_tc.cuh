@@ -285,6 +285,29 @@ __global__ void __launch_bounds__(256) pack_z_bf16_kernel(const float* __restric
   }
 }
 
+// Rated bitmap of a user list for the prepass mode of topn_tc_kernel: bit i of row r <=> item i is in
+// the train row of user users[r] (or r) OR i >= I (padded tail columns are never candidates).
+// bits [n_pad][words] must be zero; one warp per user.
+__global__ void __launch_bounds__(256) topn_bitmap_kernel(const int32_t* __restrict__ users, int n,
+                                                          const int64_t* __restrict__ row_ptr,
+                                                          const int32_t* __restrict__ col, int64_t I, int64_t words,
+                                                          uint32_t* __restrict__ bits) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const int64_t uid = users ? users[r] : r;
+  const int64_t p0 = row_ptr[uid], p1 = row_ptr[uid + 1];
+  uint32_t* row = bits + (int64_t)r * words;
+  for (int64_t p = p0 + lane; p < p1; p += 32) {
+    const int it = __ldg(col + p);
+    atomicOr(row + (it >> 5), 1u << (it & 31));
+  }
+  for (int64_t w = (I >> 5) + lane; w < words; w += 32) {
+    const int64_t first = w * 32;
+    atomicOr(row + w, first >= I ? 0xffffffffu : (0xffffffffu << (int)(I - first)));
+  }
+}
+
 // Compaction of the per-user candidate buffers, called by a whole epilogue warp with every lane
 // working on its own row: raise thr to a value t with KEEP_LO <= #{s > t} <= KEEP_HI (bisection on
 // the value) and drop the entries <= t.  thr never decreases, so "every non-candidate has
@@ -363,6 +386,8 @@ struct TcArgs {
   float* cand_thr;             // [n_users]  final threshold (every non-candidate has approx <= thr)
   const float* init_thr;       // nullable [n_users]: start threshold of each user (second pass: the
                                // first pass proved that nothing at or below it can be in the top-k)
+  const uint32_t* bits;        // nullable: rated bitmap [users_pad][words] built beforehand (rows with many rated
+  int64_t words;               //   items per tile: the in-kernel CSR walk is one dependent load per item); pad columns set
   int n_splits;                // gridDim.y: the item tiles are cut into this many contiguous ranges,
   int tiles_per_split;         //   one CTA per (user tile, range); candidates land in per-range
   int seg;                     //   segments of `seg` = CAND_MAX / n_splits slots: cand_*[(u*S + s)*seg ..]
@@ -537,7 +562,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         umma_commit(t_full + buf);
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 && a.bits == nullptr) {
     // ===== rated-item bitmaps: thread h owns rows h and h + 64 =====
     // A cursor walks each user's ascending train row once per sweep.  `cur` is the next rated item,
     // `nxt` the one after it, loaded one step AHEAD so that the tile loop never waits on a
@@ -609,7 +634,7 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         for (int c = 0; c < 8; ++c) my[c * TILE_U + h + q * 64] = w[q][c];
       mbar_arrive(b_full + buf);
     }
-  } else {
+  } else if (warp >= 4) {
     // ===== epilogue: thread = one user (TMEM lane); warp pair member `hf` takes chunks hf, hf+EPI, ..
     const int e = warp - 4;
     const int q = e & 3;                    // TMEM lane quadrant (= warp % 4)
@@ -623,13 +648,26 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int NCH = 8 / EPI;            // chunks per tile for this warp
 
+    // prepass-bitmap mode: this row's 256 rated bits of a tile are 32 contiguous bytes; tile t + 1 is
+    // fetched at the end of tile t's work
+    const bool use_bits = a.bits != nullptr;
+    const uint4* brow = use_bits ? reinterpret_cast<const uint4*>(a.bits + (int64_t)(u0 + row) * a.words) + (int64_t)t_lo * 2 : nullptr;
+    uint4 nb0 = make_uint4(0u, 0u, 0u, 0u), nb1 = nb0;
+    if (use_bits && n_t > 0) { nb0 = __ldg(brow); nb1 = __ldg(brow + 1); }
     for (int t = 0; t < n_t; ++t) {
       const int buf = t & 1;
       const uint32_t par = (t >> 1) & 1;
+      const uint4 cb0 = nb0, cb1 = nb1;
       mbar_wait(t_full + buf, par);
-      mbar_wait(b_full + buf, par);
+      if (!use_bits) mbar_wait(b_full + buf, par);
       tc_fence_after();
       const uint32_t* my_bm = bm + buf * 8 * TILE_U + row;
+      auto rated_word = [&](int c) -> uint32_t {
+        if (!use_bits) return my_bm[c * TILE_U];
+        const uint4 q = c < 4 ? cb0 : cb1;
+        const int k = c & 3;
+        return k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w;
+      };
       const int item0 = (t_lo + t) * TILE_I;
       const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I);
       // two chunks in flight: the next tcgen05.ld is issued before the current chunk is scanned
@@ -640,17 +678,18 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
         const int c0 = hf + i * EPI, c1 = hf + (i + 1) * EPI;
         tmem_ld_wait(va);
         tmem_ld32_issue(col0 + (uint32_t)(c1 * 32), vb);
-        scan_chunk<C2, KEEP_LO, KEEP_HI>(va, my_bm[c0 * TILE_U], item0 + c0 * 32, bs, bi, cnt, thr, xch, lane);
+        scan_chunk<C2, KEEP_LO, KEEP_HI>(va, rated_word(c0), item0 + c0 * 32, bs, bi, cnt, thr, xch, lane);
         tmem_ld_wait(vb);
         if (i + 2 < NCH) tmem_ld32_issue(col0 + (uint32_t)((c1 + EPI) * 32), va);
-        scan_chunk<C2, KEEP_LO, KEEP_HI>(vb, my_bm[c1 * TILE_U], item0 + c1 * 32, bs, bi, cnt, thr, xch, lane);
+        scan_chunk<C2, KEEP_LO, KEEP_HI>(vb, rated_word(c1), item0 + c1 * 32, bs, bi, cnt, thr, xch, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(t_empty + buf);
-        mbar_arrive(b_empty + buf);
+        if (!use_bits) mbar_arrive(b_empty + buf);
       }
+      if (use_bits && t + 1 < n_t) { nb0 = __ldg(brow + 2 * (t + 1)); nb1 = __ldg(brow + 2 * (t + 1) + 1); }
       // Compactions are taken TOGETHER by all epilogue warps at a tile boundary: a compaction costs
       // about as much as scanning a whole tile, and with only two accumulator buffers a warp
       // that compacts on its own stalls the MMA and, through it, the seven other warps — ~150
