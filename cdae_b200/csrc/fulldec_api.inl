@@ -100,6 +100,9 @@ static int run_fulldec(cdae_handle* h, const BatchDev& bt) {
   const bool bias_in = K_has_bias_room(h->K);
   const int K = h->K, Kp = (int)round_up(bias_in ? K + 2 : K, tc::KBLK), KB = Kp / tc::KBLK;
   const int64_t B_pad = round_up(bt.n_users, 128), I_pad = round_up(h->I, tc::TILE_I);
+  if ((double)B_pad * (double)I_pad * 2.0 > 64e9)
+    return set_error(CDAE_E_INVALID, "full_decode: the loss-gradient matrix of one minibatch (%lld users x %lld items, bf16) "
+                     "would take more than 64 GB; lower batch_users", (long long)B_pad, (long long)I_pad);
   TRY(ensure(h, h->fd_zb, (size_t)(B_pad * Kp)));
   TRY(ensure(h, h->fd_wb, (size_t)(I_pad * Kp)));
   TRY(ensure(h, h->fd_g, (size_t)(B_pad * I_pad)));

@@ -58,8 +58,13 @@ def _worker(rank, world, port, q):
         assert box[0] == bytes(range(128))
 
         out = {}
+        # the last two cases are full-item-decode training (H12): a rank's gradient carries
+        # n_rank * lambda * W' for EVERY item, and the sum over ranks must be the minibatch's n * lambda * W'
         for kw in (dict(loss="CE", beta=1.0), dict(loss="SQUARE", asymmetric=True, using_adagrad=False),
-                   dict(loss="CE", linear_function=True)):
+                   dict(loss="CE", linear_function=True),
+                   dict(loss="CE", beta=1.0, asymmetric=True, full=True), dict(loss="SQUARE", beta=1.0, full=True)):
+            kw = dict(kw)
+            full = kw.pop("full", False)
             cfg = orc.default_config(**kw)
             data = cases.small_dataset(U=150, I=300, mean=12.0, seed=11)
             U, I, K = data["U"], data["I"], cfg["num_dim"]
@@ -75,8 +80,11 @@ def _worker(rank, world, port, q):
                     dense = np.zeros(o.dense_grad_size())
                     keeps = [o.sample_keep(seed, epoch * cnum, u) for u in users]
                     ins = [col[rp[u]:rp[u + 1]][k.astype(bool)] for u, k in zip(users, keeps)]
-                    negs = [o.sample_negatives(seed, epoch * cnum, u) for u in users]
-                    o.shard_gradients(users, ins, negs, dense)
+                    if full:
+                        o.shard_gradients_full(users, ins, dense)
+                    else:
+                        negs = [o.sample_negatives(seed, epoch * cnum, u) for u in users]
+                        o.shard_gradients(users, ins, negs, dense)
                     t = torch.from_numpy(dense)
                     dist.all_reduce(t)                         # the ONE collective per minibatch
                     o.apply_dense(dense)
@@ -104,12 +112,15 @@ def _worker(rank, world, port, q):
                 single = orc.Oracle(cfg, U, I, rp, col)
                 single.set_params(p)
                 for epoch in range(2):
-                    single.train_epoch(seed, epoch, batch_users=B)
+                    if full:
+                        single.train_epoch_full(seed, epoch, B)
+                    else:
+                        single.train_epoch(seed, epoch, batch_users=B)
                 for k, v in res.items():
                     ref = single.param(k)
                     if ref.size:
                         err = float(np.abs(v - ref).max() / max(1.0, np.abs(ref).max()))
-                        out["%s/%s" % (sorted(kw.items()), k)] = err
+                        out["%s%s/%s" % (sorted(kw.items()), " full" if full else "", k)] = err
         q.put((rank, "ok", out))
     except Exception as e:  # noqa: BLE001
         import traceback
