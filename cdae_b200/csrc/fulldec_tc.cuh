@@ -119,11 +119,12 @@ __global__ void __launch_bounds__(256) fd_bitmap_kernel(const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// The epilogue is bound by issue slots and by the FMA and SFU pipes together, so sigma is computed
+// two ways, on alternating pairs of scores (FD_SIGMOID below; 598 TFLOP/s against 537 polynomial-only
+// and 558 SFU-only at config C).
 // sigma(y) for two scores at once on the FMA pipe: a = e^-|y| (one MUFU.EX2 each), then
 // 1/(1+a) on [0,1] as a degree-6 polynomial (Chebyshev fit, |rel err| < 9e-6 evaluated in fp32)
-// with packed fp32x2 FMAs; sigma(-|y|) = a/(1+a), sigma(|y|) = 1 - sigma(-|y|).  A reciprocal on
-// the SFU would make the kernel MUFU-bound (2 MUFU per score at 16/clk/SM against 0.05 clk of
-// tensor time per score at K = 200).
+// with packed fp32x2 FMAs; sigma(-|y|) = a/(1+a), sigma(|y|) = 1 - sigma(-|y|).
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -165,6 +166,17 @@ __device__ __forceinline__ void sigmoid2(float y0, float y1, float& s0, float& s
   s0 = y0 >= 0.f ? 1.f - q0 : q0;
   s1 = y1 >= 0.f ? 1.f - q1 : q1;
 }
+// sigma(y) with two SFU operations and nothing else: 1 / (1 + 2^(-y log2 e)).  ex2 saturates to
+// +inf / 0 at the ends and rcp(inf) = 0, so no clamp, no |y|, no select.
+__device__ __forceinline__ float sigmoid_sfu(float y) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + ex2_approx(-1.4426950408889634f * y)));
+  return r;
+}
+#ifndef FD_SIGMOID
+#define FD_SIGMOID 2   // 0: polynomial on the FMA pipe, 1: SFU reciprocal, 2: alternate pairs, 3: 3 of 4 pairs on the SFU, 4: 1 of 4
+                       // (A/B: CDAE_NVCC_FLAGS=-DFD_SIGMOID=n)
+#endif
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -202,7 +214,12 @@ __device__ __forceinline__ void grad_compute(const uint32_t (&v)[32], uint32_t p
     const float t1 = __uint_as_float(((pos >> (j + 1)) & 1u) * 0x3f800000u);
     float g0, g1;
     if (LT == LOSS_CE) {             // loss.hpp:141-147: sigma(y) - t
-      sigmoid2(y0, y1, g0, g1);
+      if (FD_SIGMOID == 1 || (FD_SIGMOID == 2 && (j & 2)) || (FD_SIGMOID == 3 && (j & 6)) || (FD_SIGMOID == 4 && !(j & 6))) {
+        g0 = sigmoid_sfu(y0);
+        g1 = sigmoid_sfu(y1);
+      } else {
+        sigmoid2(y0, y1, g0, g1);
+      }
       g0 -= t0;
       g1 -= t1;
     } else {                         // SQUARE, loss.hpp:53-55: -2 (t - y)
