@@ -53,10 +53,27 @@ static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorM
   static bool attr_set = false;
   const size_t dyn = fd::gemm_smem(KB);
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
+  // CDAE_B200_FD_GEMM_CLUSTER=1: pairs of output tiles share the B stream (Wb / Zb slabs of each
+  // contraction step) through 2-CTA clusters with multicast TMA.  Parity-identical, measured neutral
+  // (hidden 0.412 vs 0.404 ms, item gradient 0.484 vs 0.482 ms per two launches at config C): both
+  // kernels are bound by reading G from HBM (62-68 % of the nominal peak = ~80 % of the measured copy
+  // bandwidth, profiles/r01_q_*), not by the B stream out of L2.
+  static const bool cl_on = getenv("CDAE_B200_FD_GEMM_CLUSTER") && atoi(getenv("CDAE_B200_FD_GEMM_CLUSTER")) != 0;
+  if (!cl_on || grid.x % 2 != 0) {
+    fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT, false><<<grid, 256, dyn, h->stream>>>(ma, mb, a);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = dyn; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT, true>, ma, mb, a));
   return 0;
 }
 template <int KB, int LT>

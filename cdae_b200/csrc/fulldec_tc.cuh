@@ -729,7 +729,10 @@ struct GemmArgs {
 // One CTA = one 128-row output tile x all Kp columns (accumulator: Kp TMEM columns), walking its
 // share of the contraction in steps of 64 through a GM_STAGE-deep TMA ring.
 // warp 0 TMA · warp 1 MMA issue · warp 2 TMEM owner · warps 4-7 epilogue (thread = output row).
-template <int KB, bool ITEMGRAD, bool BOUT = false>
+// CL2: clusters of two CTAs (adjacent output tiles, same share of the contraction) read the SAME
+// B slabs (Wb / Zb rows of the contraction step); each fetches every other 64-column box and
+// multicasts it into both shared memories, halving the B stream out of L2.
+template <int KB, bool ITEMGRAD, bool BOUT = false, bool CL2 = false>
 __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b, GemmArgs a) {
   constexpr int STAGE_BYTES = GM_A_BYTES + KB * GM_BOX_BYTES;
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GM_STAGE; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
+      mbar_init(empty + s, CL2 ? 2 : 1);
     }
     mbar_init(t_full, 1);
     fence_barrier_init();
@@ -773,6 +776,8 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
+  if (CL2) cluster_sync_all();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -791,8 +796,11 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
           // G: rows = the tile's 128 users, 128 bytes = items k0..k0+63
           tma_load_2d(st, &map_a, full + s, k0, m0);
         }
-        for (int kb = 0; kb < KB; ++kb)   // rows = contraction index, 128 bytes = columns kb*64..
-          tma_load_2d(st + GM_A_BYTES + kb * GM_BOX_BYTES, &map_b, full + s, kb * KBLK, k0);
+        for (int kb = 0; kb < KB; ++kb) {   // rows = contraction index, 128 bytes = columns kb*64..
+          if (!CL2) tma_load_2d(st + GM_A_BYTES + kb * GM_BOX_BYTES, &map_b, full + s, kb * KBLK, k0);
+          else if ((uint32_t)(kb & 1) == crank)
+            tma_load_2d_mc(st + GM_A_BYTES + kb * GM_BOX_BYTES, &map_b, full + s, kb * KBLK, k0, (uint16_t)0x3);
+        }
         if (++s == GM_STAGE) { s = 0; ph ^= 1; }
       }
     }
@@ -816,7 +824,8 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
             umma_bf16(tmem_base + ONES_COL, ad, umma_desc_mn_sw128(smem_u32(sOnes) + k * 2048, GM_BOX_BYTES), idesc1, (t | k) != 0);
           }
         }
-        umma_commit(empty + s);
+        if (CL2) umma_commit_mc(empty + s, (uint16_t)0x3);
+        else umma_commit(empty + s);
         if (++s == GM_STAGE) { s = 0; ph ^= 1; }
       }
       umma_commit(t_full);
@@ -877,6 +886,7 @@ __global__ void __launch_bounds__(256, 1) fd_gemm_kernel(const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, TCOLS);
   }
+  if (CL2) cluster_sync_all();
 }
 
 }  // namespace fd
