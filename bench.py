@@ -201,6 +201,12 @@ def run_ours(args):
         uid = [CDAE.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         m.dist_init(rank, world, uid[0])
+        if os.environ.get("CDAE_B200_P2P") == "1":          # opt-in: NVLink peer-memory all-reduce instead of NCCL
+            def gather(b):
+                box = [None] * world
+                dist.all_gather_object(box, b)
+                return box
+            m.dist_p2p_init(gather)
     m.init_params(SEED)
     rp_pin, col_pin = m.pinned_array(rp), m.pinned_array(col)
 
@@ -294,7 +300,8 @@ def run_ours(args):
                            "train_nnz": int(len(col)), "batch_users": batch_users,
                            "step": "one epoch = CDAE::train_one_iteration over all users",
                            "l2": "256 MB flush write between timed iterations",
-                           "parallelism": "dp%d (users sharded, 1 all-reduce of dense item gradients per minibatch)" % world,
+                           "parallelism": "dp%d (users sharded, 1 all-reduce of dense item gradients per minibatch%s)" % (
+                               world, ", NVLink peer-memory kernel" if os.environ.get("CDAE_B200_P2P") == "1" else ", NCCL" if world > 1 else ""),
                            "loss_last_epoch": loss},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},

@@ -68,6 +68,8 @@ SIGNATURES = {
     "cdae_topn_evaluate": (C.c_int, [C.c_void_p, i64p, i32p, f64p, i64p]),
     "cdae_dist_unique_id": (C.c_int, [C.c_void_p]),
     "cdae_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "cdae_dist_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cdae_dist_p2p_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cdae_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "cdae_profile_get": (C.c_int, [C.c_void_p, f64p, i64p]),
     "cdae_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

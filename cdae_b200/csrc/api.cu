@@ -17,6 +17,7 @@
 #include "topn_kernels.cuh"
 #include "topn_tc.cuh"
 #include "fulldec_tc.cuh"
+#include "p2p_allreduce.cuh"
 #include "train_kernels.cuh"
 
 using namespace cdae;
@@ -425,7 +426,19 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleA
   // CDAE_B200_DEBUG_SKIP_ALLREDUCE=1: measurement aid only (ranks diverge) — isolates the cost of
   // the collective in a scaling run
   static const bool skip_allreduce = getenv("CDAE_B200_DEBUG_SKIP_ALLREDUCE") != nullptr;
-  if (h->world > 1 && !skip_allreduce) {
+  if (h->world > 1 && !skip_allreduce && h->p2p_on) {
+    // two-shot all-reduce over NVLink peer memory (p2p_allreduce.cuh) + the barrier before apply
+    ProfScope ps(h, CDAE_K_ALLREDUCE);
+    p2p::Args pa;
+    for (int r = 0; r < p2p::MAX_RANKS; ++r) { pa.bufs[r] = h->p2p_bufs[r]; pa.flags[r] = h->p2p_flags[r]; }
+    pa.rank = h->rank; pa.world = h->world; pa.n4 = (int64_t)(h->grad_floats / 4);
+    pa.epoch = ++h->p2p_epoch;
+    p2p::reduce_kernel<<<h->sm_count, 512, 0, h->stream>>>(pa);
+    KERNEL_OK(h);
+    pa.epoch = ++h->p2p_epoch;
+    p2p::barrier_kernel<<<1, 32, 0, h->stream>>>(pa);
+    KERNEL_OK(h);
+  } else if (h->world > 1 && !skip_allreduce) {
     ProfScope ps(h, CDAE_K_ALLREDUCE);
     NC(g_nccl.AllReduce(h->grad.p, h->grad.p, h->grad_floats, kNcclFloat, kNcclSum,
                         (ncclComm_t)h->comm, h->stream));
@@ -614,6 +627,12 @@ int cdae_destroy(cdae_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
+  for (int r = 0; r < 8; ++r) {
+    if (r == h->rank) continue;
+    if (h->p2p_bufs[r]) cudaIpcCloseMemHandle(h->p2p_bufs[r]);
+    if (h->p2p_flags[r]) cudaIpcCloseMemHandle(h->p2p_flags[r]);
+  }
+  if (h->p2p_my_flags) cudaFree(h->p2p_my_flags);
   ModelDev& m = h->m;
   float* tabs[] = {m.W, m.V, m.Wu, m.b, m.bp, m.Uu, m.W_ag, m.V_ag, m.Wu_ag, m.b_ag, m.bp_ag, m.Uu_ag};
   for (float* p : tabs) if (p) cudaFree(p);
@@ -970,6 +989,47 @@ int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl
   h->comm = comm;
   h->rank = rank; h->world = world;
   h->plan_valid = false;
+  return 0;
+}
+
+int cdae_dist_p2p_export(cdae_handle* h, void* out128) {
+  if (!h || !out128) return set_error(CDAE_E_INVALID, "NULL argument");
+  if (h->world < 2 || h->world > p2p::MAX_RANKS) return set_error(CDAE_E_STATE, "needs a process group of 2..%d ranks (cdae_dist_init first)", p2p::MAX_RANKS);
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->p2p_my_flags) {
+    CU(cudaMalloc(&h->p2p_my_flags, 64 * sizeof(uint32_t)));
+    CU(cudaMemset(h->p2p_my_flags, 0, 64 * sizeof(uint32_t)));
+  }
+  cudaIpcMemHandle_t hg, hf;
+  CU(cudaIpcGetMemHandle(&hg, h->grad.p));
+  CU(cudaIpcGetMemHandle(&hf, h->p2p_my_flags));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out128, &hg, 64);
+  memcpy((char*)out128 + 64, &hf, 64);
+  return 0;
+}
+
+int cdae_dist_p2p_open(cdae_handle* h, const void* handles) {
+  if (!h || !handles) return set_error(CDAE_E_INVALID, "NULL argument");
+  if (h->world < 2 || h->world > p2p::MAX_RANKS || !h->p2p_my_flags) return set_error(CDAE_E_STATE, "cdae_dist_p2p_export has not run on this rank");
+  CU(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) {
+      h->p2p_bufs[r] = h->grad.p;
+      h->p2p_flags[r] = h->p2p_my_flags;
+      continue;
+    }
+    cudaIpcMemHandle_t hg, hf;
+    memcpy(&hg, (const char*)handles + (size_t)r * 128, 64);
+    memcpy(&hf, (const char*)handles + (size_t)r * 128 + 64, 64);
+    void *pg = nullptr, *pf = nullptr;
+    CU(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    h->p2p_bufs[r] = (float*)pg;
+    h->p2p_flags[r] = (uint32_t*)pf;
+  }
+  h->p2p_epoch = 0;
+  h->p2p_on = true;
   return 0;
 }
 

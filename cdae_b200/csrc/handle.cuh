@@ -42,6 +42,12 @@ struct cdae_handle {
   int ch_in = 64, ch_out = 16;
   int rank = 0, world = 1;
   void* comm = nullptr;  // ncclComm_t
+  // NVLink peer-memory all-reduce (p2p_allreduce.cuh), opt-in through cdae_dist_p2p_open
+  bool p2p_on = false;
+  float* p2p_bufs[8] = {nullptr};
+  uint32_t* p2p_flags[8] = {nullptr};
+  uint32_t* p2p_my_flags = nullptr;
+  uint32_t p2p_epoch = 0;
   int sm_count = 148;
   size_t dev_bytes = 0;
 

@@ -269,6 +269,15 @@ class CDAE:
         buf = C.create_string_buffer(unique_id, 128)
         _lib.check(self._L.cdae_dist_init(self._h, rank, world, buf))
 
+    def dist_p2p_init(self, all_gather):
+        """Switch the gradient all-reduce to the NVLink peer-memory kernel.  `all_gather(bytes) ->
+        list of bytes in rank order` is the caller's collective (e.g. torch.distributed.all_gather_object)."""
+        buf = (C.c_char * 128)()
+        _lib.check(self._L.cdae_dist_p2p_export(self._h, buf))
+        table = b"".join(all_gather(bytes(buf)))
+        tb = C.create_string_buffer(table, len(table))
+        _lib.check(self._L.cdae_dist_p2p_open(self._h, tb))
+
     def save(self, path):
         """Versioned binary checkpoint of every parameter block incl. AdaGrad state (cdae_save)."""
         _lib.check(self._L.cdae_save(self._h, str(path).encode()))

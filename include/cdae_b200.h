@@ -221,6 +221,15 @@ int cdae_load(cdae_handle* h, const char* path);
 int cdae_dist_unique_id(void* id128_out);
 int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id);
 
+/* Optional: replace the per-minibatch NCCL all-reduce by a two-shot all-reduce over NVLink peer
+ * memory written for this path (csrc/p2p_allreduce.cuh): every rank exports CUDA IPC handles of its
+ * gradient buffer and flag array (128 bytes), the caller gathers them in rank order (world x 128
+ * bytes) and hands the table to every rank.  Needs cdae_dist_init first, 2..8 ranks on one node with
+ * peer access; every rank must open before the next training call.  NCCL remains in use for
+ * everything else (parameter read-back, data_loss). */
+int cdae_dist_p2p_export(cdae_handle* h, void* handles128_out);
+int cdae_dist_p2p_open(cdae_handle* h, const void* all_handles);
+
 /* Per-kernel-class device timing for benchmarks: when enabled, every kernel launch is
  * bracketed by CUDA events on the handle's stream; cdae_profile_get returns, per class,
  * the summed milliseconds and the number of launches since cdae_profile(h, 1). */

@@ -57,9 +57,13 @@ def _run(rank, world, local, failures):
     # on tcgen05 and adds n_rank*lambda*W' to its gradient, the all-reduce makes that n*lambda*W'
     for kw in (dict(loss="CE", beta=1.0, num_dim=50), dict(loss="SQUARE", asymmetric=True, num_dim=20),
                dict(loss="CE", user_factor=False, num_dim=33),
-               dict(loss="CE", beta=1.0, asymmetric=True, num_dim=100, full_decode=True)):
+               dict(loss="CE", beta=1.0, asymmetric=True, num_dim=100, full_decode=True),
+               # the same reduction through the NVLink peer-memory all-reduce instead of NCCL
+               dict(loss="CE", beta=1.0, num_dim=50, p2p=True),
+               dict(loss="SQUARE", asymmetric=True, num_dim=20, p2p=True)):
         kw = dict(kw)
         full = kw.pop("full_decode", False)
+        use_p2p = kw.pop("p2p", False)
         cfg = orc.default_config(**kw)
         data = cases.small_dataset(U=403, I=500, mean=12.0, seed=5)
         U, I, K = data["U"], data["I"], cfg["num_dim"]
@@ -70,6 +74,12 @@ def _run(rank, world, local, failures):
         uid = [CDAE.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         m.dist_init(rank, world, uid[0])
+        if use_p2p:
+            def gather(b):
+                box = [None] * world
+                dist.all_gather_object(box, b)
+                return box
+            m.dist_p2p_init(gather)
         m.set_params(p)
         steps = 0
         for epoch in range(3):
@@ -98,7 +108,7 @@ def _run(rank, world, local, failures):
                 err = np.abs(v - ref).max() / max(1e-12, np.abs(ref).max())
                 # full decode: three epochs of bf16 rounding flips (tests/test_gpu_fulldec.py) on top of fp32 order
                 if not err <= (3e-3 if full else 2e-4):
-                    failures.append("%s %s: max err %.3g" % (kw, k, err))
+                    failures.append("%s%s %s: max err %.3g" % (kw, " p2p" if use_p2p else "", k, err))
             keep = np.concatenate([o.sample_keep(7, 0x80000000, u) for u in range(U)])
             ref_loss = o.data_loss(keep)
             if not abs(loss - ref_loss) <= 2e-4 * abs(ref_loss):
