@@ -9,7 +9,7 @@ static int encode_all_users(cdae_handle* h) {
   // ONE gather over every input chunk of this rank (the work-item list is contiguous across
   // minibatches) accumulating straight into topn_z rows addressed by global uid, then ONE
   // in-place activate: 100,000 users per launch instead of 8192 keeps the gather near its
-  // bandwidth bound (profiles/r01_e_*).
+  // bandwidth bound.
   int64_t n_in = 0, n_users = 0;
   for (const MiniBatch& p : h->plan) { n_in += p.n_in; n_users += p.n_users; }
   if (n_users == 0) return 0;
