@@ -1,7 +1,7 @@
 """N2 measurement: "user item" text -> training structure, native loader (cdae_dataset_load_pairs:
 text -> CSR) vs the reference (Data::load -> vector<Instance>, then RecsysModelBase::reset -> hash of
 hashes; verbatim headers through oracle/_ref, which also allocates the model's parameters).
-CPU only.  usage: python tools/loader_bench.py [users items mean]"""
+CPU only.  usage: python tests/experiments/loader_bench.py [users items mean]"""
 import ctypes as C
 import os
 import resource
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from cdae_b200 import Dataset, synth  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
