@@ -5,8 +5,8 @@
 // in place of decode_kernel; everything before (gather, activate) and after (hidden_backward,
 // scatter, all-reduce, apply) is the sampled path's.
 
-// The widest split of `units` pieces of work over CTAs of `tiles` output tiles that still fills
-// whole waves of the device: maximise tiles*S / (ceil(tiles*S / SMs) * SMs), S <= max_s.
+// How many CTAs share the `units` pieces of work of each of `tiles` output tiles: wave efficiency of a
+// split S is tiles*S / (ceil(tiles*S / SMs) * SMs); the smallest S within 8 % of the best one wins.
 static int fd_pick_split(int tiles, int units, int min_units, int sms, int max_s) {
   double eff[64];
   double best_eff = 0.;
