@@ -62,3 +62,18 @@ def test_sass_has_vector_reductions(built):
     sass = subprocess.run(["cuobjdump", "-sass", built], capture_output=True, text=True).stdout
     assert "REDG.E.ADD.F32x4" in sass
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", built], capture_output=True, text=True).stdout
+
+
+def test_sass_is_blackwell_native(built):
+    """The tensor-core paths must compile to tcgen05 / TMA / TMEM instructions (no mma.sync
+    fallback): UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor load / store (.MULTICAST: the
+    2-CTA cluster variants), LDTM = tcgen05.ld, UTCBAR = tcgen05.commit; the full-decode epilogue
+    uses packed fp32x2 FMAs (FFMA2) and both SFU operations; the peer-memory all-reduce uses
+    system-scope acquire / release accesses."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", built], capture_output=True, text=True).stdout
+    for op in ("UTCHMMA", "UTMALDG.2D", "UTMALDG.2D.MULTICAST", "UTMASTG.2D", "LDTM.x32", "UTCBAR", "UTCBAR.MULTICAST",
+               "FFMA2", "MUFU.EX2", "MUFU.RCP", "UCGABAR_ARV"):
+        assert op in sass, op
+    assert "HMMA" not in sass.replace("UTCHMMA", "")            # no warp-level mma.sync anywhere
+    assert ".STRONG.SYS" in sass                                # ld.acquire.sys / st.release.sys of the p2p flags
