@@ -1,15 +1,26 @@
 #!/usr/bin/env python
 """users/sec of CDAE training (BASELINE.json metric) on N B200s, plus the CPU reference arm.
 
-A step = ONE EPOCH (CDAE::train_one_iteration, cdae.hpp:136-146) over the synthetic config-B
-set: 100,000 users x 50,000 items per GPU (weak scaling: U = 100,000 * N), ~30 train items per
-user, K=50, num_neg=5, q=0.5 scaled, CROSS_ENTROPY, lambda=.01, lr=.1, AdaGrad beta=1, tied
-weights, user factor on.  `value` times the epoch with the CSR resident in HBM
-(CUDA events on the engine's stream); `e2e` times cdae_train_epoch_csr, which takes the CSR from
-pinned HOST memory on every call and reads the epoch statistics back.
+A step = ONE EPOCH (CDAE::train_one_iteration, cdae.hpp:136-146) over a synthetic data set of one of
+BASELINE.json's configurations (weak scaling: the per-GPU user count is fixed):
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            (torchrun for N > 1)
+  B  (default, the configuration the metric is quoted on)  100,000 users per GPU x 50,000 items,
+     ~30 train items per user, K=50, num_neg=5, tied weights, sampled decode
+  C  138,000 users x 27,000 items, ~145 items per user, K=200, FULL-item decode (tcgen05), asymmetric
+  D  1M x 200K over 8 GPUs = 125,000 users per GPU x 200,000 items, K=100, num_neg=5, tied
+  E  500K x 100K over 8 GPUs = 62,500 users per GPU x 100,000 items, K=256, full-item decode
+
+all with q=0.5 scaled, CROSS_ENTROPY, lambda=.01, lr=.1, AdaGrad beta=1, user factor on.  `value`
+times the epoch with the CSR resident in HBM (CUDA events on the engine's stream, no per-kernel
+events in that region); `e2e` times cdae_train_epoch_csr, which takes the CSR from pinned HOST
+memory on every call and reads the epoch statistics back; a third, profiled pass over the same
+inputs gives the per-kernel times the roofline is computed from.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config B|C|D|E]      (torchrun for N > 1)
   python bench.py --impl reference ...   the reference's own CPU path (oracle/_ref)
+
+Without --config the line is config B and carries the other configurations as `configs`: C (full
+138K users) at N = 1; D and E (their per-GPU shards) at N = 8 (or with --extra D,E at any N).
 """
 import argparse
 import json
@@ -25,40 +36,63 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-METRIC = "users/sec CDAE training (K=50, Yelp-scale)"
 UNIT = "users/s"
-USERS_PER_GPU = 100_000
-ITEMS = 50_000
-MEAN_ITEMS = 30.0
-K, NUM_NEG = 50, 5
 SEED = 20141119
 
-MODEL_CFG = dict(lambda_=0.01, learn_rate=0.1, corruption_ratio=0.5, beta=1.0, loss="CE",
-                 num_dim=K, num_neg=NUM_NEG, num_corruptions=1, using_adagrad=True,
-                 asymmetric=False, user_factor=True, linear=False, scaled=True,
-                 linear_function=False, tanh=False)
+CONFIGS = {
+    "B": dict(users_per_gpu=100_000, items=50_000, mean=30.0, K=50, num_neg=5, asym=False, full=False,
+              batch=8192, gpus=1, metric="users/sec CDAE training (K=50, Yelp-scale)",
+              what="synthetic %dK users x 50K items, K=50, neg-sample=5, %dxB200"),
+    "C": dict(users_per_gpu=138_000, items=27_000, mean=145.0, K=200, num_neg=5, asym=True, full=True,
+              batch=0, gpus=1, metric="users/sec CDAE training (K=200, MovieLens-20M-scale, full-item decode)",
+              what="MovieLens-20M-scale synthetic (%dK x 27K), K=200, full-item decode, %dxB200"),
+    "D": dict(users_per_gpu=125_000, items=200_000, mean=30.0, K=100, num_neg=5, asym=False, full=False,
+              batch=8192, gpus=8, metric="users/sec CDAE training (K=100, Yelp-scale 1M x 200K)",
+              what="Yelp-scale synthetic %dK x 200K, K=100, neg-sample=5, user-sharded %dxB200"),
+    "E": dict(users_per_gpu=62_500, items=100_000, mean=50.0, K=256, num_neg=5, asym=True, full=True,
+              batch=0, gpus=8, metric="users/sec CDAE training (K=256, 500K x 100K, full-item decode bf16)",
+              what="full-item decode %dK x 100K, K=256, bf16 tcgen05 path, %dxB200"),
+}
 
 
-def workload_name(n_gpus):
-    return ("synthetic %dK users x %dK items, K=%d, neg-sample=%d, %dxB200"
-            % (USERS_PER_GPU * n_gpus // 1000, ITEMS // 1000, K, NUM_NEG, n_gpus))
+def model_cfg(c):
+    return dict(lambda_=0.01, learn_rate=0.1, corruption_ratio=0.5, beta=1.0, loss="CE",
+                num_dim=c["K"], num_neg=c["num_neg"], num_corruptions=1, using_adagrad=True,
+                asymmetric=c["asym"], user_factor=True, linear=False, scaled=True,
+                linear_function=False, tanh=False)
 
 
-def measured_peaks():
-    """(HBM GB/s, bf16 TFLOP/s burst, source) — driver-measured, else the profiling recipe's fallback."""
+def config_dict(name, world, batch_users_global, sms=148):
+    """The `config` object of the JSON line — the same function serves both arms, so the reference
+    arm and ours describe one workload."""
+    c = CONFIGS[name]
+    U = c["users_per_gpu"] * world
+    return {"workload": c["what"] % (U // 1000, world), "name": name, "users": U, "items": c["items"],
+            "mean_train_items_per_user": c["mean"], "num_dim": c["K"],
+            "decode": "all items" if c["full"] else "positives + %d sampled negatives each" % c["num_neg"],
+            "weights": "asymmetric" if c["asym"] else "tied", "loss": "CE", "optimizer": "AdaGrad beta=1, lr=0.1, lambda=0.01",
+            "corruption": "q=0.5, scaled", "step": "one epoch = CDAE::train_one_iteration over all users",
+            "seed": SEED}
+
+
+def peaks():
+    """Driver-measured peaks (MEASURED_PEAKS.json), else the profiling recipe's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 def decode_kernel_name(K):
     """The <G,NV> instantiation DISPATCH_LD (csrc/api.cu) picks for this K."""
-    lines = ((K + 31) // 32 * 32) // 32
+    lines = (K + 31) // 32
+    lines = lines if lines <= 4 else 6 if lines <= 6 else 8 if lines <= 8 else 12 if lines <= 12 else 16
     g, nv = ((8, lines) if lines <= 4 else (16, 3) if lines <= 6 else (16, 4) if lines <= 8
              else (32, 3) if lines <= 12 else (32, 4))
-    return "decode_kernel<%d,%d,TRAIN,SAMPLED>" % (g, nv)
+    return "decode_kernel<%d,%d,TRAIN,SAMPLED,CE>" % (g, nv), lines * 32
 
 
 def ncu_traffic(kernel):
@@ -82,7 +116,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -116,59 +150,129 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_reference_rate(data, n_sample, steps=1, warmup=0, quiet=True):
-    """users/s of the reference's own (single-threaded, fp64) train loop on the first n_sample
-    users.  Uses oracle/_ref (the verbatim reference headers) when that library exists, else the
-    C port.  Returns (value, info)."""
+# data
+def rank_dataset(name, rank, world, batch_global):
+    """This rank's view of the configuration's data set.  One GPU: the whole set.  A process group:
+    only the rows of the users the rank trains are generated (an independent block per rank over one
+    shared item popularity model); the other users' rows are empty in its CSR."""
+    from cdae_b200 import synth
+    c = CONFIGS[name]
+    U = c["users_per_gpu"] * world
+    if world == 1:
+        if name == "B":
+            return synth.make_dataset(U, c["items"], c["mean"], seed=SEED)       # the r01 arrays
+        return synth.make_blocked_dataset(U, c["items"], c["mean"], seed=SEED)
+    return synth.make_sharded_dataset(U, c["items"], c["mean"], batch_global, rank, world, seed=SEED)
+
+
+# --------------------------------------------------------------------------------------------
+# the CPU arm
+def cpu_reference_rate(name, data, n_sample, steps=1, warmup=0, quiet=True):
+    """users/s of the reference's own (single-threaded, fp64) train loop on the first n_sample users.
+    Sampled decode (B, D): the VERBATIM reference headers (oracle/_ref; the default build and a
+    -march=x86-64-v3 build are both timed, the faster one is reported), else the C port.  Full-item
+    decode (C, E) has no reference function: the oracle's full mode is timed.
+    Returns (value, info, times)."""
     from oracle import oracle as orc
+    c = CONFIGS[name]
+    mcfg = model_cfg(c)
     rp, col = data["train_row_ptr"], data["train_col"]
     n = int(min(n_sample, data["U"]))
-    sub_rp = np.ascontiguousarray(rp[:n + 1])
-    sub_col = np.ascontiguousarray(col[:rp[n]])
-    if orc.have_reference():
-        col2, i_seen = orc.first_seen_relabel(sub_rp, sub_col)
-        ref = orc.Reference(MODEL_CFG, n, i_seen, sub_rp, col2, quiet=quiet)
-        orc.Reference.seed(SEED, SEED)
-        times = [ref.train_user_range(0, n) for _ in range(warmup + steps)][warmup:]
-        kind = "reference"
-        how = ("verbatim reference headers (oracle/_ref, Eigen/Boost/glog stand-ins), first %d of "
-               "%d users, %d of %d items seen, 1 thread (the reference trains single-threaded)"
-               % (n, data["U"], i_seen, data["I"]))
-    else:
-        o = orc.Oracle(MODEL_CFG, data["U"], data["I"], rp, col)
+    if c["full"]:
+        o = orc.Oracle(mcfg, data["U"], data["I"], rp, col)
         o.init_params(SEED)
         times = []
         for s in range(warmup + steps):
             t = time.perf_counter()
-            o.train_epoch(SEED, s, 1, 0, n)
+            o.train_epoch_full(SEED, s, n, 0, 0, n)
             times.append(time.perf_counter() - t)
         times = times[warmup:]
-        kind = "port"
-        how = "C port of the reference loop (oracle/), first %d of %d users, 1 thread" % (n, data["U"])
-    return n * len(times) / sum(times), dict(kind=kind, cores=1, sample=how), times
+        info = dict(kind="port", cores=1,
+                    sample="C port of the frozen-batch step with all items as outputs (oracle/; the reference has no "
+                           "full-item-decode training), first %d of %d users as one minibatch, fp64, 1 thread" % (n, data["U"]))
+        return n * len(times) / sum(times), info, times
+    sub_rp = np.ascontiguousarray(rp[:n + 1])
+    sub_col = np.ascontiguousarray(col[:rp[n]])
+    if orc.have_reference():
+        col2, i_seen = orc.first_seen_relabel(sub_rp, sub_col)
+        builds = [(so, label) for so, label in ((orc.REF_SO, "-O3"), (orc.REF_V3_SO, "-O3 -march=x86-64-v3")) if os.path.exists(so)]
+        if len(builds) > 1:                                  # pick the faster build on a 1,000-user prefix
+            k = min(n, 1000)
+            k_rp, k_col = np.ascontiguousarray(rp[:k + 1]), np.ascontiguousarray(col[:rp[k]])
+            k_col2, k_seen = orc.first_seen_relabel(k_rp, k_col)
+            trial = []
+            for so, label in builds:
+                ref = orc.Reference(mcfg, k, k_seen, k_rp, k_col2, quiet=quiet, so=so)
+                orc.Reference.seed(SEED, SEED, so=so)
+                trial.append(min(ref.train_user_range(0, k) for _ in range(2)))
+                del ref
+            builds = [builds[int(np.argmin(trial))]]
+        so, label = builds[0]
+        ref = orc.Reference(mcfg, n, i_seen, sub_rp, col2, quiet=quiet, so=so)
+        orc.Reference.seed(SEED, SEED, so=so)
+        times = [ref.train_user_range(0, n) for _ in range(warmup + steps)][warmup:]
+        rate = n * len(times) / sum(times)
+        info = dict(kind="reference", cores=1, build="g++ " + label + " (the faster of the builds present)",
+                    sample="verbatim reference headers (oracle/_ref; Eigen/Boost/glog are this repo's stand-ins: "
+                           "plain loops, real Eigen may differ), first %d of %d users = %d of %d items seen (ids relabelled), "
+                           "fp64, 1 thread (the reference trains single-threaded, cdae.hpp:136-146)"
+                           % (n, data["U"], i_seen, data["I"]))
+        return rate, info, times
+    o = orc.Oracle(mcfg, data["U"], data["I"], rp, col)
+    o.init_params(SEED)
+    times = []
+    for s in range(warmup + steps):
+        t = time.perf_counter()
+        o.train_epoch(SEED, s, 1, 0, n)
+        times.append(time.perf_counter() - t)
+    times = times[warmup:]
+    info = dict(kind="port", cores=1, sample="C port of the reference loop (oracle/), first %d of %d users, 1 thread" % (n, data["U"]))
+    return n * len(times) / sum(times), info, times
+
+
+def cpu_multicore_rate(name, data, n_sample):
+    """BASELINE.md §3 baseline (ii): OUR Hogwild port of the reference loop (oracle/, fp64, lock-free
+    user-parallel over all host cores) — labelled as a port, the reference itself has no parallel trainer."""
+    from oracle import oracle as orc
+    c = CONFIGS[name]
+    if c["full"]:
+        return None
+    cores = os.cpu_count() or 1
+    n = int(min(n_sample * min(cores, 16), data["U"]))
+    o = orc.Oracle(model_cfg(c), data["U"], data["I"], data["train_row_ptr"], data["train_col"])
+    o.init_params(SEED)
+    o.train_epoch_hogwild(SEED, 0, cores, 0, min(n, 2000))                      # thread start-up
+    t = time.perf_counter()
+    o.train_epoch_hogwild(SEED, 1, cores, 0, n)
+    dt = time.perf_counter() - t
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port",
+                sample="oracle/ Hogwild (lock-free user-parallel) port of the reference loop, fp64, first %d of %d users, %d threads"
+                       % (n, data["U"], cores))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from cdae_b200 import synth
     from oracle import oracle as orc
     orc.build(ref=False)
-    data = synth.make_dataset(USERS_PER_GPU, ITEMS, MEAN_ITEMS, seed=SEED)
+    name = args.config or "B"
+    c = CONFIGS[name]
+    data = rank_dataset(name, 0, 1, 0)
     # calibrate so that the whole (warmup + steps) run stays within ~2 minutes
-    rate, _, _ = cpu_reference_rate(data, 1000)
+    rate, _, _ = cpu_reference_rate(name, data, 64 if c["full"] else 1000)
     total = max(1, args.steps + args.warmup)
-    n = int(max(500, min(USERS_PER_GPU, rate * 120.0 / total)))
-    value, info, times = cpu_reference_rate(data, n, args.steps, args.warmup)
+    # (the 1,000-user calibration runs cache-resident and over-estimates the rate of a longer prefix by ~2x)
+    n = int(max(16 if c["full"] else 500, min(c["users_per_gpu"], args.cpu_sample, rate * 40.0 / total)))
+    value, info, times = cpu_reference_rate(name, data, n, args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
     info["value"] = value
     info["unit"] = UNIT
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+    info["sample_users_per_step"] = n
+    line = {"impl": "reference", "metric": c["metric"], "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(1), "sample_users_per_step": n},
+            "data": "synthetic", "config": config_dict(name, 1, 0),
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -177,40 +281,45 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
-def run_ours(args):
+# our arm
+class Ctx:
+    pass
+
+
+def measure(name, ctx, args, primary):
+    """One configuration on this process group: returns (result dict for rank 0, data set)."""
     import torch
     import torch.distributed as dist
-    from cdae_b200 import CDAE, CDAEConfig, synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            sys.exit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    U = USERS_PER_GPU * world
-    data = synth.make_dataset(U, ITEMS, MEAN_ITEMS, seed=SEED)   # same arrays on every rank
+    from cdae_b200 import CDAE, CDAEConfig
+    c = CONFIGS[name]
+    world, rank, local = ctx.world, ctx.rank, ctx.local
+    sms = ctx.sms
+    batch_per_gpu = c["batch"] if c["batch"] > 0 else 128 * sms
+    if name == "B" and args.batch_users:
+        batch_per_gpu = args.batch_users
+    batch_global = batch_per_gpu * world                        # weak scaling: the global minibatch grows with N
+    U, I, K = c["users_per_gpu"] * world, c["items"], c["K"]
+    mcfg = model_cfg(c)
+    data = rank_dataset(name, rank, world, batch_global)
     rp, col = data["train_row_ptr"], data["train_col"]
-    batch_users = args.batch_users * world                        # global minibatch, weak scaling
-    m = CDAE(CDAEConfig(batch_users=batch_users, device=local, **MODEL_CFG)).reset(U, ITEMS, rp, col)
+    m = CDAE(CDAEConfig(batch_users=batch_global, device=local, full_decode=c["full"], **mcfg)).reset(U, I, rp, col)
+    allreduce = "none"
     if world > 1:
         uid = [CDAE.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         m.dist_init(rank, world, uid[0])
-        if os.environ.get("CDAE_B200_P2P") == "1":          # opt-in: NVLink peer-memory all-reduce instead of NCCL
+        allreduce = "NCCL all-reduce + replicated apply"
+        if ctx.p2p:
             def gather(b):
                 box = [None] * world
                 dist.all_gather_object(box, b)
                 return box
             m.dist_p2p_init(gather)
+            allreduce = ctx.p2p_label
     m.init_params(SEED)
     rp_pin, col_pin = m.pinned_array(rp), m.pinned_array(col)
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    steps = args.steps if primary else max(3, min(args.steps, 5))
+    warmup = args.warmup if primary else max(3, min(args.warmup, 3))
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,25 +329,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def one_epoch(epoch, host_csr):
-        flush.zero_()                       # L2 flush between timed iterations (untimed)
+        ctx.flush.zero_()                   # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
         t = time.perf_counter()
-        st = m.train_one_iteration(seed=SEED, epoch=epoch,
-                                   csr=(rp_pin, col_pin) if host_csr else None)
+        st = m.train_one_iteration(seed=SEED, epoch=epoch, csr=(rp_pin, col_pin) if host_csr else None)
         return st, time.perf_counter() - t
 
     epoch = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_epoch(epoch, False)
         epoch += 1
     # ---- timed region 1: CSR resident in HBM, device time (CUDA events on the engine stream)
-    m.profile(True)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and primary) else None
     barrier()
     t0 = time.perf_counter()
-    dev_ms, launches, outputs, users = 0.0, 0, 0, 0
-    loss = 0.0
-    for _ in range(args.steps):
+    dev_ms, launches, outputs, users, loss = 0.0, 0, 0, 0, 0.0
+    for _ in range(steps):
         st, _w = one_epoch(epoch, False)
         epoch += 1
         dev_ms += st.device_ms
@@ -249,20 +355,29 @@ def run_ours(args):
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if sampler else None
-    prof = m.profile_get()
-    m.profile(False)
     # ---- timed region 2: end to end through the host-CSR call (wall clock incl. H2D + D2H)
-    for _ in range(min(2, args.warmup)):
+    for _ in range(2):
         one_epoch(epoch, True)
         epoch += 1
     barrier()
     e2e_s, h2d, d2h = 0.0, 0, 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         st, w = one_epoch(epoch, True)
         epoch += 1
         e2e_s += w
         h2d, d2h = st.h2d_bytes, st.d2h_bytes
     barrier()
+    # ---- region 3: the same epochs with an event pair around every kernel launch (per-kernel times)
+    m.profile(True)
+    prof_ms, prof_out = 0.0, 0
+    for _ in range(steps):
+        st, _w = one_epoch(epoch, False)
+        epoch += 1
+        prof_ms += st.device_ms
+        prof_out += st.outputs
+    barrier()
+    prof = m.profile_get()
+    m.profile(False)
 
     tv = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([users, outputs, launches], dtype=torch.float64, device="cuda")
@@ -271,62 +386,104 @@ def run_ours(args):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms = tv.tolist()
     users_all, outputs_all, launches_all = cnt.tolist()
+    res = None
     if rank == 0:
+        pk = peaks()
         value = users_all / (dev_ms / 1e3)
-        e2e = users_all / (e2e_ms / 1e3)
-        peak, peak_tf, peak_src = measured_peaks()
-        # dominant kernel: sampled decode.  Algorithmic bytes:
-        # outputs * (P*4K + P*4 + 4), P = 4 row passes with AdaGrad.
-        dec_ms, dec_n = prof["decode"]
-        P = 4 if MODEL_CFG["using_adagrad"] else 2
-        out_rank0 = outputs_all / world
-        alg_bytes = out_rank0 * (P * 4 * K + P * 4 + 4)
-        achieved = alg_bytes / (dec_ms / 1e3) / 1e9 if dec_ms > 0 else None
-        traffic, traffic_src = ncu_traffic("decode_kernel")
-        roofline = {"bound": "hbm", "kernel": decode_kernel_name(K), "achieved": achieved,
-                    "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak if achieved else None, "traffic": traffic,
-                    "traffic_source": traffic_src,
-                    "note": "item tables + gradients (38 MB) are L2-resident: DRAM traffic is far below the "
-                            "algorithmic bytes, so frac on algorithmic bytes can exceed 1",
-                    "launches": dec_n, "avg_launch_ms": dec_ms / dec_n if dec_n else None,
-                    "algorithmic_bytes_per_launch": alg_bytes / dec_n if dec_n else None,
-                    "kernel_ms_share": {k: v[0] / dev_ms for k, v in prof.items() if v[1]}}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": workload_name(world), "users": U, "items": ITEMS,
-                           "train_nnz": int(len(col)), "batch_users": batch_users,
-                           "step": "one epoch = CDAE::train_one_iteration over all users",
-                           "l2": "256 MB flush write between timed iterations",
-                           "parallelism": "dp%d (users sharded, 1 all-reduce of dense item gradients per minibatch%s)" % (
-                               world, ", NVLink peer-memory kernel" if os.environ.get("CDAE_B200_P2P") == "1" else ", NCCL" if world > 1 else ""),
-                           "loss_last_epoch": loss},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
-        if world == 1 and not args.no_topn:
-            line["topn"] = topn_section(m, U, peak_tf, peak_src)
-        if world == 1 and not args.no_fulldecode:
-            m.close()                                          # free config B before the config-C-shaped run
-            line["fulldecode"] = fulldecode_section(local, peak_tf, peak_src)
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as orc
-            orc.build(ref=False)
-            v, info, _ = cpu_reference_rate(data, args.cpu_sample)
-            info["value"] = v
-            info["unit"] = UNIT
-            line["cpu_baseline"] = info
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+        share = {k: v[0] / prof_ms for k, v in prof.items() if v[1]}
+        res = {"metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16 operands, f32 accumulate (f32 everywhere outside the decode)" if c["full"] else "f32",
+               "data": "synthetic"}
+        cfgd = config_dict(name, world, batch_global, sms)
+        res["config"] = cfgd
+        res["run"] = {"train_nnz_rank0": int(len(col)), "batch_users_global": batch_global, "batch_users_per_gpu": batch_per_gpu,
+                      "l2": "256 MB flush write between timed iterations",
+                      "parallelism": "dp%d: users sharded, item-side gradients combined once per minibatch (%s)" % (world, allreduce),
+                      "loss_last_epoch_rank0": loss}
+        res["e2e"] = {"value": users_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / steps}
+        res["gpu_launches"] = int(launches_all)
+        if clocks is not None:
+            res["clocks"] = clocks
+        res["kernel_ms_share"] = share
+        res["kernel_share_note"] = ("from a separate profiled pass (event pair around every launch, %.3f ms per step against "
+                                    "%.3f unprofiled)" % (prof_ms / steps, dev_ms / steps))
+        if c["full"]:
+            res["roofline"] = tensor_roofline(c, prof, steps, users_all / world, dev_ms / steps, pk)
+        else:
+            res["roofline"] = decode_roofline(m, c, prof, prof_out, pk)
+    ctx.last_model = m
+    return res, data
 
 
-def topn_section(m, U, peak_tf, peak_src):
+def decode_roofline(m, c, prof, outputs_profiled, pk):
+    """The dominant kernel of the sampled path.  §8(d) algorithmic bytes: outputs * (P*4K + P*4 + 4),
+    P = 4 row passes with AdaGrad.  When the item tables + gradients fit the L2 (config B: 38 MB of 126)
+    the kernel does not move those bytes through HBM, so the bound is the L2: `peak` is then measured
+    live by cdae_probe_l2 (the same row loads + vector reductions, nothing else) and `achieved` counts
+    the bytes the kernel really requests from L2 (padded rows: one read + one reduction per output)."""
+    K, I = c["K"], c["items"]
+    kname, ld = decode_kernel_name(K)
+    dec_ms, dec_n = prof["decode"]
+    if not dec_n:
+        return None
+    out_per_launch = outputs_profiled / dec_n
+    avg_ms = dec_ms / dec_n
+    alg = out_per_launch * (4 * 4 * K + 4 * 4 + 4)
+    l2_bytes = out_per_launch * (2 * ld * 4 + 12)               # row read + row reduction (+ b' read, gb' reduction, item id)
+    working_set = I * ld * 4 * 3
+    visits = int(out_per_launch)
+    both, both_ms = m.probe_l2(I, 3, visits)
+    rd, _ = m.probe_l2(I, 1, visits)
+    red, _ = m.probe_l2(I, 2, visits)
+    traffic, traffic_src = ncu_traffic("decode_kernel" if c["items"] == 50_000 else "decode_kernel_D")
+    l2_resident = working_set < 100e6
+    ach_alg = alg / (avg_ms / 1e3) / 1e9
+    ach_l2 = l2_bytes / (avg_ms / 1e3) / 1e9
+    r = {"kernel": kname, "launches": dec_n, "avg_launch_ms": avg_ms, "unit": "GB/s",
+         "algorithmic_bytes_per_launch": alg, "achieved_algorithmic": ach_alg,
+         "hbm_peak": pk["hbm"], "peak_source": pk["source"],
+         "l2_bytes_per_launch": l2_bytes, "achieved_l2": ach_l2,
+         "peak_l2": both, "peak_l2_read_only": rd, "peak_l2_reduction_only": red,
+         "peak_l2_source": "cdae_probe_l2 run by this process: uniformly random rows of a %d x %d fp32 table, ld.v4 + red.v4 per row, "
+                           "same lane geometry, %d row visits per launch (%.3f ms)" % (I, ld, visits, both_ms),
+         "working_set_bytes": working_set, "traffic": traffic, "traffic_source": traffic_src}
+    if l2_resident:
+        r.update({"bound": "l2", "achieved": ach_l2, "peak": both, "frac": ach_l2 / both,
+                  "note": "W + its AdaGrad state + the gradient buffer (%.0f MB) are L2-resident, so the §8(d) algorithmic bytes never "
+                          "reach HBM (achieved_algorithmic / hbm_peak = %.2f is NOT a roofline fraction); the governing roofline is the "
+                          "L2's load + vector-reduction throughput, measured by the probe" % (working_set / 1e6, ach_alg / pk["hbm"])})
+    else:
+        r.update({"bound": "hbm", "achieved": ach_alg, "peak": pk["hbm"], "frac": ach_alg / pk["hbm"],
+                  "frac_of_probe": ach_l2 / both,
+                  "note": "working set %.0f MB exceeds the 126 MB L2; frac_of_probe compares with the pure load + reduction "
+                          "kernel on the same table size" % (working_set / 1e6)})
+    return r
+
+
+def tensor_roofline(c, prof, steps, users_rank, step_ms, pk):
+    """Full-item decode: the three tcgen05 contractions, 6*I*K flops per user, against the
+    SUSTAINED bf16 peak (the kernels run back to back inside a long step)."""
+    per = {k: v[0] / steps for k, v in prof.items() if v[1]}
+    tens = [k for k in ("fd_score", "fd_hidden", "fd_itemgrad") if k in per]
+    tens_ms = sum(per[k] for k in tens)
+    flops = 6.0 * users_rank * c["items"] * c["K"]
+    ach = flops / (tens_ms / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": " + ".join(tens), "achieved": ach, "peak": pk["tf_sustained"],
+            "peak_source": pk["source"] + ", sustained", "peak_burst": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": ach / pk["tf_sustained"], "flops": "6*U*I*K per epoch (SURVEY 8d), per GPU",
+            "per_kernel_ms_per_epoch": per,
+            "per_kernel_tflops": {k: (flops / 3.0) / (per[k] / 1e3) / 1e12 for k in tens},
+            "whole_step_tflops": flops / (step_ms / 1e3) / 1e12,
+            "whole_step_frac": flops / (step_ms / 1e3) / 1e12 / pk["tf_sustained"],
+            "traffic": ncu_traffic("fd_gemm_kernel")[0]}
+
+
+def topn_section(m, c, U, pk):
     """Secondary measurement (not part of the timed training step): CDAE::recommend for all users,
     i.e. the full-item decode on tcgen05 (csrc/topn_tc.cuh), against the measured bf16 peak."""
+    K, ITEMS = c["K"], c["items"]
     m.pre_recommend(10)                                       # warm-up (allocations, tensor maps)
     m.profile(True)
     reps = 3
@@ -338,67 +495,74 @@ def topn_section(m, U, peak_tf, peak_src):
     ms = prof["topn"][0] / reps
     kp = (K + 2 + 63) // 64 * 64
     alg = 2.0 * U * ITEMS * K                                  # 2*I*K flops per user
-    out = {"what": "CDAE::recommend, all users x all items, top-10 (cdae_topn_build)",
-           "path": "tcgen05 bf16 + exact fp64 re-rank" if path == 1 else "fp32 CUDA cores",
-           "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank", "topn_exact")) / reps / 1e3),
-           "candidate_kernel_ms": ms, "verified_users": verified, "redone_exact_users": redone,
-           "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel<%d>" % (kp // 64),
-                        "achieved": alg / (ms / 1e3) / 1e12 if ms > 0 else None, "peak": peak_tf,
-                        "peak_source": peak_src + ", burst", "unit": "TFLOP/s",
-                        "frac": alg / (ms / 1e3) / 1e12 / peak_tf if ms > 0 else None,
-                        "executed_tflops_padded_k": 2.0 * U * ITEMS * kp / (ms / 1e3) / 1e12 if ms > 0 else None,
-                        "traffic": ncu_traffic("topn_tc_kernel")[0]}}
-    return out
+    return {"what": "CDAE::recommend, all users x all items, top-10 (cdae_topn_build)",
+            "path": "tcgen05 bf16 + exact fp64 re-rank" if path == 1 else "fp32 CUDA cores",
+            "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank", "topn_exact")) / reps / 1e3),
+            "candidate_kernel_ms": ms, "verified_users": verified, "redone_exact_users": redone,
+            "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel<%d>" % (kp // 64),
+                         "achieved": alg / (ms / 1e3) / 1e12 if ms > 0 else None, "peak": pk["tf_burst"],
+                         "peak_source": pk["source"] + ", burst", "unit": "TFLOP/s",
+                         "frac": alg / (ms / 1e3) / 1e12 / pk["tf_burst"] if ms > 0 else None,
+                         "executed_tflops_padded_k": 2.0 * U * ITEMS * kp / (ms / 1e3) / 1e12 if ms > 0 else None,
+                         "scores_per_s": U * ITEMS / (ms / 1e3) if ms > 0 else None,
+                         "traffic": ncu_traffic("topn_tc_kernel")[0]}}
 
 
-def fulldecode_section(device, peak_burst, peak_src):
-    """Secondary measurement: full-item-decode TRAINING (BASELINE.json configs[2]:
-    138K x 27K, K=200, full-item decode, 1xB200) — the three tcgen05 contractions of
-    csrc/fulldec_tc.cuh inside the complete training step.  Bounded to the first 4 frozen
-    minibatches' worth of users of that shape (128 x SM count users each) so the default bench run
-    stays short; per-user cost does not depend on U."""
-    from cdae_b200 import CDAE, CDAEConfig, synth
+def run_ours(args):
     import torch
-    sms = torch.cuda.get_device_properties(device).multi_processor_count
-    Uc, Ic, Kc, mean = 4 * 128 * sms, 27_000, 200, 145.0
-    d = synth.make_dataset(Uc, Ic, mean_train=mean, seed=SEED)
-    cfg = CDAEConfig(lambda_=0.01, learn_rate=0.1, corruption_ratio=0.5, beta=1.0, loss="CE", num_dim=Kc,
-                     using_adagrad=True, asymmetric=True, user_factor=True, scaled=True,
-                     full_decode=True, device=device)
-    m = CDAE(cfg).reset(Uc, Ic, d["train_row_ptr"], d["train_col"])
-    m.init_params(SEED)
-    for ep in range(2):
-        m.train_one_iteration(seed=SEED, epoch=ep)
-    m.profile(True)
-    reps, ms = 3, []
-    for ep in range(2, 2 + reps):
-        ms.append(m.train_one_iteration(seed=SEED, epoch=ep).device_ms)
-    prof = m.profile_get()
-    m.profile(False)
+    import torch.distributed as dist
+
+    ctx = Ctx()
+    ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
+    ctx.local = local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.exit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx.sms = torch.cuda.get_device_properties(local).multi_processor_count
+    ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    p2p_env = os.environ.get("CDAE_B200_P2P", "")
+    ctx.p2p = world > 1 and (p2p_env == "1" or args.allreduce == "p2p")
+    ctx.p2p_label = "NVLink peer-memory kernel"
+
+    primary = args.config or "B"
+    extras = []
+    if args.extra:
+        extras = [x for x in args.extra.split(",") if x and x != primary]
+    elif not args.config and not args.no_extra:
+        extras = ["C"] if world == 1 else ["D", "E"] if world == 8 else []
+    line, data = measure(primary, ctx, args, True)
+    m = ctx.last_model
+    c = CONFIGS[primary]
+    if rank == 0:
+        if world == 1 and primary == "B" and not args.no_topn:
+            line["topn"] = topn_section(m, c, c["users_per_gpu"], peaks())
     m.close()
-    per = {k: v[0] / reps for k, v in prof.items() if v[1]}
-    fused = "fd_hidden" not in per                              # default: score + hidden gradient in one kernel
-    tens = [k for k in ("fd_score", "fd_hidden", "fd_itemgrad") if k in per]
-    tens_ms = sum(per[k] for k in tens)
-    flops = 6.0 * Uc * Ic * Kc                                 # SURVEY 8d: 6*I*K per user
-    d_peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    peak_sus = float(d_peaks.get("bf16_tflops_sustained", 1400.0))
-    step_ms = float(np.median(ms))
-    ach = flops / (tens_ms / 1e3) / 1e12
-    return {"what": "CDAE training with full-item decode (targets 1 on the train row, 0 elsewhere), bf16 tcgen05, fp32 accumulate",
-            "workload": "config C shape: %d users (4 minibatches of 128 x %d SMs; BASELINE's 138K bounded) x %d items, K=%d, mean %d train items/user, asymmetric, CE, AdaGrad"
-                        % (Uc, sms, Ic, Kc, int(mean)),
-            "users_per_s": Uc / (step_ms / 1e3), "ms_per_epoch": step_ms,
-            "kernel_ms_per_epoch": per,
-            "roofline": {"bound": "tensor", "kernel": ("fd_fused_kernel (scores + loss gradient + hidden gradient) + fd_gemm_kernel<itemgrad>" if fused
-                                    else "fd_score_kernel + fd_gemm_kernel<hidden> + fd_gemm_kernel<itemgrad>"),
-                         "achieved": ach, "peak": peak_sus,
-                         "peak_source": peak_src + ", sustained (timed inside a long step)",
-                         "unit": "TFLOP/s", "frac": ach / peak_sus,
-                         "flops": "6*U*I*K (SURVEY 8d)", "peak_burst": peak_burst,
-                         "per_kernel_tflops": {k: (2.0 if (fused and k == "fd_score") else 1.0) * (flops / 3.0) / (per[k] / 1e3) / 1e12 for k in tens},
-                         "whole_step_tflops": flops / (step_ms / 1e3) / 1e12,
-                         "traffic": ncu_traffic("fd_gemm_kernel")[0]}}
+    ctx.last_model = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.build(ref=False)
+        v, info, _ = cpu_reference_rate(primary, data, args.cpu_sample if not c["full"] else 48)
+        info["value"] = v
+        info["unit"] = UNIT
+        line["cpu_baseline"] = info
+        mc = cpu_multicore_rate(primary, data, args.cpu_sample)
+        if mc:
+            line["cpu_baseline_multicore"] = mc
+    del data
+    for name in extras:
+        res, _d = measure(name, ctx, args, False)
+        ctx.last_model.close()
+        ctx.last_model = None
+        if rank == 0:
+            line.setdefault("configs", {})[name] = res
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 class OneLineStdout:
@@ -431,12 +595,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-users", type=int, default=8192, help="users per minibatch per GPU")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json configuration (default B)")
+    ap.add_argument("--extra", default=None, help="comma list of further configurations to add under `configs`")
+    ap.add_argument("--no-extra", action="store_true", help="only the primary configuration")
+    ap.add_argument("--batch-users", type=int, default=0, help="config B: users per minibatch per GPU (default 8192)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p"])
     ap.add_argument("--cpu-sample", type=int, default=30000,
                     help="users in the bounded CPU-baseline sample (about 10-15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-topn", action="store_true", help="skip the recommend (full-item decode) section")
-    ap.add_argument("--no-fulldecode", action="store_true", help="skip the full-item-decode training section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

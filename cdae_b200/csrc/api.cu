@@ -19,6 +19,7 @@
 #include "fulldec_tc.cuh"
 #include "p2p_allreduce.cuh"
 #include "train_kernels.cuh"
+#include "probe_kernels.cuh"
 
 using namespace cdae;
 
@@ -254,6 +255,7 @@ static int build_plan(cdae_handle* h) {
   CU(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
   h->plan_max_slots = max_slots;
   h->plan_max_users = max_users;
+  h->plan_n_uids = uids.size();
   h->plan_valid = true;
   return 0;
 }
@@ -420,7 +422,7 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleA
     TRY(launch_scatter(h, bt));
   }
   if (h->m.linear_function && bt.n_users > 0) {
-    uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt);
+    uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt, h->stats_d);
     KERNEL_OK(h);
   }
   // CDAE_B200_DEBUG_SKIP_ALLREDUCE=1: measurement aid only (ranks diverge) — isolates the cost of
@@ -457,6 +459,7 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleA
   a.seg[a.nseg++] = ApplySeg{h->m.b, h->m.b_ag, h->m.gb, h->ld / 4, h->m.lambda, nullptr, 0.f, 1};
   a.cnt_clear = h->m.gcnt + (int64_t)(h->m.steps_slot ^ 1) * h->I4;
   a.n_cnt = h->I4;
+  a.bad_csr_out = &h->stats_d->bad_csr;
   apply_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(a);
   KERNEL_OK(h);
   h->m.steps_slot ^= 1;  // apply cleared the other slot for the next minibatch
@@ -496,6 +499,10 @@ static int end_call(cdae_handle* h, cdae_epoch_stats_t* stats) {
     stats->h2d_bytes = h->h2d;
     stats->d2h_bytes = h->d2h;
   }
+  if (h->stats_h->bad_csr) h->csr_bad = true;
+  if (h->stats_h->bad_csr)
+    return set_error(CDAE_E_INVALID, "the CSR passed to cdae_train_epoch_csr has an item id outside [0,%lld) or a row that is "
+                     "not strictly ascending; no parameter was updated", (long long)h->I);
   if (h->stats_h->bad_loss)
     return set_error(CDAE_E_NUMERIC, "LOGISTIC loss received a score outside (0,1) "
                      "(the reference CHECK-aborts here, loss.hpp:96; use CROSS_ENTROPY)");
@@ -527,6 +534,10 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   if (cfg->num_neg < 0 || cfg->num_neg > DECODE_MAX_NEGS || cfg->num_corruptions < 1)
     return set_error(CDAE_E_INVALID, "0 <= num_neg <= %d and num_corruptions >= 1 required", DECODE_MAX_NEGS);
   if (cfg->loss_type < 0 || cfg->loss_type > CDAE_LOSS_LOGM) return set_error(CDAE_E_INVALID, "unknown loss_type %d", cfg->loss_type);
+  if (!std::isfinite(cfg->corruption_ratio) || cfg->corruption_ratio < 0. || cfg->corruption_ratio > 1.)
+    return set_error(CDAE_E_INVALID, "corruption_ratio must be in [0,1], got %g", cfg->corruption_ratio);
+  if (!std::isfinite(cfg->lambda) || cfg->lambda < 0. || !std::isfinite(cfg->learn_rate) || !std::isfinite(cfg->beta) || cfg->beta < 0.)
+    return set_error(CDAE_E_INVALID, "lambda >= 0, beta >= 0 and a finite learn_rate are required");
   if (row_ptr[U] >= 0x7fffffff) return set_error(CDAE_E_INVALID, "nnz must be < 2^31");
   if (cfg->full_decode) {
     if (cfg->loss_type != CDAE_LOSS_CROSS_ENTROPY && cfg->loss_type != CDAE_LOSS_SQUARE)
@@ -565,7 +576,9 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   memset(&m, 0, sizeof(m));
   m.I = I; m.U = U; m.K = h->K; m.ld = h->ld;
   m.lambda = (float)cfg->lambda; m.lr = (float)cfg->learn_rate; m.beta = (float)cfg->beta;
-  m.scale = cfg->scaled ? (float)(1. / (1. - cfg->corruption_ratio)) : 1.f;  // cdae.hpp:202-205
+  // cdae.hpp:202-205.  q == 1: the reference's scale is inf but its input set is always empty, so the
+  // factor is never multiplied (:366, :377-380) — scale 1 gives the same hidden values without inf * 0.
+  m.scale = (cfg->scaled && cfg->corruption_ratio < 1.) ? (float)(1. / (1. - cfg->corruption_ratio)) : 1.f;
   m.loss = cfg->loss_type; m.nu = cfg->num_neg;
   m.adagrad = cfg->using_adagrad; m.asym = cfg->asymmetric; m.user_factor = cfg->user_factor;
   m.linear = cfg->linear; m.tanh_act = cfg->tanh_act; m.linear_function = cfg->linear_function;
@@ -659,6 +672,7 @@ int cdae_destroy(cdae_handle* h) {
 int cdae_init_params(cdae_handle* h, uint64_t seed) {
   if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
   CU(cudaSetDevice(h->cfg.device));
+  h->topn_k = 0;  // stored recommendation lists are stale
   const double scale = 4. * std::sqrt(6. / (double)(h->I + h->K));
   struct { float* p; int64_t rows; uint32_t which; } blocks[3] = {
       {h->m.W, h->I, CDAE_P_W}, {h->m.V, h->I, CDAE_P_V}, {h->m.Wu, h->U, CDAE_P_WU}};
@@ -691,6 +705,7 @@ int cdae_set_param(cdae_handle* h, int which, const double* src, int64_t n) {
   if (which < 0 || which >= CDAE_P_COUNT) return set_error(CDAE_E_INVALID, "unknown parameter block %d", which);
   if (n != r * c) return set_error(CDAE_E_INVALID, "block %d holds %lld values, got %lld", which, (long long)(r * c), (long long)n);
   if (n == 0) return 0;
+  h->topn_k = 0;  // stored recommendation lists are stale
   const bool vec_bp = which == CDAE_P_BPRIME || which == CDAE_P_BPRIME_AG;
   TRY(ensure(h, h->stage_d, (size_t)n));
   CU(cudaMemcpyAsync(h->stage_d.p, src, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
@@ -764,7 +779,23 @@ int cdae_get_param_rows(cdae_handle* h, int which, const int64_t* rows, int64_t 
 }
 
 static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats) {
+  h->topn_k = 0;  // stored recommendation lists are stale
   if (!h->plan_valid) TRY(build_plan(h));
+  if (h->csr_unchecked) {
+    // cdae_train_epoch_csr: the caller's CSR was uploaded without a host pass over it.  One warp per
+    // trained user checks it on the device (item ids in range — out-of-range ids are clamped in the
+    // device copy so no kernel can index outside a table — and rows strictly ascending); a violation
+    // raises stats->bad_csr and the shared flag g_steps[2], which make hidden_backward / uu_update /
+    // apply skip their updates, and the call returns CDAE_E_INVALID with the parameters untouched.
+    CU(cudaMemsetAsync(h->m.g_steps + 2, 0, sizeof(float), h->stream));
+    const int64_t n = (int64_t)h->plan_n_uids;
+    if (n > 0) {
+      validate_rows_kernel<<<cdiv(n * 32, 256), 256, 0, h->stream>>>(h->plan_uids.p, n, h->row_ptr_d.p, h->col_d.p,
+                                                                 h->I, h->stats_d, h->m.g_steps + 2);
+      KERNEL_OK(h);
+    }
+    h->csr_unchecked = false;
+  }
   TRY(ensure_scratch(h, h->plan_max_users, h->plan_max_slots));
   const int cnum = h->cfg.num_corruptions;
   for (const MiniBatch& p : h->plan) {
@@ -780,6 +811,7 @@ static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_e
 
 int cdae_train_epoch(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats) {
   if (!h) return set_error(CDAE_E_INVALID, "handle is NULL");
+  if (h->csr_bad) return set_error(CDAE_E_STATE, "the resident CSR failed validation in the last cdae_train_epoch_csr; pass a valid one");
   TRY(begin_call(h));
   return train_epoch_impl(h, seed, epoch, stats);
 }
@@ -808,6 +840,11 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
     }
   }
   if (!same_rows) {
+    // row_ptr is small (U + 1 entries) and the work lists are cut from it on the host: check it here;
+    // col (nnz entries) is checked on the device after the upload (validate_rows_kernel)
+    if (row_ptr[0] != 0) return set_error(CDAE_E_INVALID, "row_ptr[0] must be 0");
+    for (int64_t u = 0; u < h->U; ++u)
+      if (row_ptr[u + 1] < row_ptr[u]) return set_error(CDAE_E_INVALID, "row_ptr not monotone at user %lld", (long long)u);
     h->row_ptr_h.assign(row_ptr, row_ptr + h->U + 1);
     h->nnz = nnz;
     h->plan_valid = false;
@@ -827,6 +864,8 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
       h->h2d += sizeof(int64_t) * (p.n_users + 1) + sizeof(int32_t) * (s1 - s0);
     }
   }
+  h->csr_unchecked = true;
+  h->csr_bad = false;
   return train_epoch_impl(h, seed, epoch, stats);
 }
 
@@ -857,6 +896,7 @@ int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8
   if (!h || !uids || n <= 0) return set_error(CDAE_E_INVALID, "need a non-empty uid list");
   if (h->world > 1) return set_error(CDAE_E_STATE, "cdae_train_users is single-process (explicit inputs)");
   TRY(begin_call(h));
+  h->topn_k = 0;  // stored recommendation lists are stale
   int64_t slots = 0, n_in = 0, n_out = 0;
   TRY(stage_users(h, uids, n, true, &slots, &n_in, &n_out));
   if (slots > 0 && !keep_mask) return set_error(CDAE_E_INVALID, "keep_mask is NULL");
@@ -1046,6 +1086,57 @@ int cdae_profile_get(cdae_handle* h, double* ms_out, int64_t* launches_out) {
   return 0;
 }
 
+// The L2 roofline of the sampled decode's access pattern (probe_kernels.cuh): `row_visits` uniformly
+// random rows of a rows x ld table are read with 16-byte vector loads (mode & 1) and / or receive a
+// 16-byte vector reduction into a second table (mode & 2), in the handle's own <G,NV> row geometry.
+int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits, int32_t reps,
+                  double* gbs_out, double* ms_out) {
+  if (!h || !gbs_out || rows <= 0 || row_visits <= 0 || reps <= 0 || mode < 1 || mode > 3)
+    return set_error(CDAE_E_INVALID, "bad argument");
+  CU(cudaSetDevice(h->cfg.device));
+  const int ld = h->ld;
+  float *src = nullptr, *dst = nullptr, *sink = nullptr;
+  const size_t bytes = sizeof(float) * (size_t)rows * ld;
+  CU(cudaMalloc(&src, bytes));
+  CU(cudaMalloc(&dst, bytes));
+  CU(cudaMalloc(&sink, 16));
+  CU(cudaMemsetAsync(src, 0, bytes, h->stream));
+  CU(cudaMemsetAsync(dst, 0, bytes, h->stream));
+  const int rows_per_warp = 192;                    // one output chunk of the decode: <= 96 rows, two chunks' worth
+  const int n_warps = (int)((row_visits + rows_per_warp - 1) / rows_per_warp);
+  const int grid = cdiv((int64_t)n_warps * 32, 256);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  int rc = 0;
+  for (int it = 0; it < reps + 2 && rc == 0; ++it) {  // two warm-up launches bring both tables into L2
+    if (it == 2) CU(cudaEventRecord(e0, h->stream));
+#define CALL(G, NV)                                                                                              \
+    do {                                                                                                           \
+      if (mode == 1) l2_probe_kernel<G, NV, 1><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
+      else if (mode == 2) l2_probe_kernel<G, NV, 2><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
+      else l2_probe_kernel<G, NV, 3><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
+    } while (0)
+    DISPATCH_LD(ld, CALL);
+#undef CALL
+    if (cudaGetLastError() != cudaSuccess) rc = set_error(CDAE_E_CUDA, "probe launch failed");
+  }
+  float ms = 0.f;
+  if (rc == 0) {
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(src); cudaFree(dst); cudaFree(sink);
+  if (rc) return rc;
+  const double per = ms / reps;
+  const double moved = (double)n_warps * rows_per_warp * ld * 4.0 * ((mode & 1) + ((mode >> 1) & 1));
+  *gbs_out = moved / (per * 1e-3) / 1e9;
+  if (ms_out) *ms_out = per;
+  return 0;
+}
+
 int cdae_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes < 0) return set_error(CDAE_E_INVALID, "bad argument");
   CU(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
@@ -1071,10 +1162,8 @@ int cdae_stream(cdae_handle* h, void** stream_out) {
 // Phase A of recommend: per-user candidate lists (TOPN_M best by score).
 static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users) {
   const size_t dyn = (size_t)TT_U * TOPN_M * (sizeof(float) + sizeof(int));
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the CURRENT device (several handles / devices per process)
     CU(cudaFuncSetAttribute(topn_tile_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
   }
   ProfScope ps(h, CDAE_K_TOPN_EXACT);
   topn_tile_fp32_kernel<<<cdiv(n_users, TT_U), 256, dyn, h->stream>>>(

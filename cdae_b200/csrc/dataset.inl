@@ -182,49 +182,83 @@ int cdae_dataset_free(cdae_dataset* d) {
   return 0;
 }
 
-// ---- model checkpoint: "CDAEB200" | version | config | U, I, K | per present block: id, rows, cols, doubles
+// ---- model checkpoint (version 2):
+//   "CDAEB200" | u32 version | config, field by field at fixed widths (4 x f64, 15 x i32) | i64 U, I, K |
+//   per present block: i64 id, rows, cols, rows*cols doubles | i64 -1, 0, 0
+// (version 1 wrote the raw cdae_config_t, whose layout depends on the compiler's padding.)
 static const char kCkptMagic[8] = {'C', 'D', 'A', 'E', 'B', '2', '0', '0'};
+static const uint32_t kCkptVersion = 2;
 
+static void ckpt_cfg_pack(const cdae_config_t& c, double d[4], int32_t i[15]) {
+  d[0] = c.lambda; d[1] = c.learn_rate; d[2] = c.corruption_ratio; d[3] = c.beta;
+  const int32_t v[15] = {c.loss_type, c.num_dim, c.num_neg, c.num_corruptions, c.using_adagrad, c.asymmetric,
+                         c.user_factor, c.linear, c.scaled, c.linear_function, c.tanh_act, c.batch_users,
+                         c.full_decode, 0, 0};
+  memcpy(i, v, sizeof(v));
+}
+
+// In a process group cdae_save is COLLECTIVE: the user-private blocks (Wu, Uu and their accumulators)
+// are assembled from their owners (cdae_get_param all-reduces them), so every rank must call it; only
+// rank 0 touches `path`.
 int cdae_save(cdae_handle* h, const char* path) {
   if (!h || !path) return set_error(CDAE_E_INVALID, "NULL argument");
-  FILE* f = fopen(path, "wb");
-  if (!f) return set_error(CDAE_E_INVALID, "cannot open %s for writing", path);
-  const uint32_t version = 1;
+  const bool writer = h->rank == 0;
+  FILE* f = writer ? fopen(path, "wb") : nullptr;
+  int open_failed = (writer && !f) ? 1 : 0;
+  // every rank must take the same number of collective steps: the writer reports "cannot open" after them
+  double cd[4];
+  int32_t ci[15];
+  ckpt_cfg_pack(h->cfg, cd, ci);
   const int64_t dims[3] = {h->U, h->I, h->K};
-  bool ok = fwrite(kCkptMagic, 1, 8, f) == 8 && fwrite(&version, 4, 1, f) == 1 &&
-            fwrite(&h->cfg, sizeof(cdae_config_t), 1, f) == 1 && fwrite(dims, sizeof(dims), 1, f) == 1;
+  bool ok = true;
+  if (f)
+    ok = fwrite(kCkptMagic, 1, 8, f) == 8 && fwrite(&kCkptVersion, 4, 1, f) == 1 && fwrite(cd, sizeof(cd), 1, f) == 1 &&
+         fwrite(ci, sizeof(ci), 1, f) == 1 && fwrite(dims, sizeof(dims), 1, f) == 1;
   std::vector<double> buf;
-  for (int which = 0; ok && which < CDAE_P_COUNT; ++which) {
+  int rc = 0;
+  for (int which = 0; which < CDAE_P_COUNT; ++which) {
     int64_t r = 0, c = 0;
     if (cdae_param_shape(h, which, &r, &c) != 0) { ok = false; break; }
     const int64_t n = r * c;
     if (n == 0) continue;
     buf.resize((size_t)n);
-    const int rc = cdae_get_param(h, which, buf.data(), n);
-    if (rc != 0) { fclose(f); return rc; }
-    const int64_t hdr[3] = {which, r, c};
-    ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(buf.data(), sizeof(double), (size_t)n, f) == (size_t)n;
+    rc = cdae_get_param(h, which, buf.data(), n);
+    if (rc != 0) break;
+    if (f && ok) {
+      const int64_t hdr[3] = {which, r, c};
+      ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(buf.data(), sizeof(double), (size_t)n, f) == (size_t)n;
+    }
   }
-  const int64_t tail[3] = {-1, 0, 0};
-  ok = ok && fwrite(tail, sizeof(tail), 1, f) == 1;
-  if (fclose(f) != 0) ok = false;
+  if (f) {
+    const int64_t tail[3] = {-1, 0, 0};
+    ok = ok && fwrite(tail, sizeof(tail), 1, f) == 1;
+    if (fclose(f) != 0) ok = false;
+  }
+  if (rc != 0) return rc;
+  if (open_failed) return set_error(CDAE_E_INVALID, "cannot open %s for writing", path);
   return ok ? 0 : set_error(CDAE_E_INVALID, "short write to %s", path);
 }
 
+// Restores every parameter block (incl. AdaGrad state).  The hyper-parameters of the HANDLE stay in
+// force: the structural ones (shape, asymmetric, user_factor, linear_function) must match the file, a
+// difference in the others (lambda, learn_rate, ...) is legal — resuming with a new learning rate is
+// the usual reason — and is reported through cdae_last_error() with return code 0.  In a process
+// group every rank loads the same file (each keeps the rows it owns up to date).
 int cdae_load(cdae_handle* h, const char* path) {
   if (!h || !path) return set_error(CDAE_E_INVALID, "NULL argument");
   FILE* f = fopen(path, "rb");
   if (!f) return set_error(CDAE_E_INVALID, "cannot open %s", path);
   char magic[8];
   uint32_t version = 0;
-  cdae_config_t cfg;
+  double cd[4], hd[4];
+  int32_t ci[15], hi[15];
   int64_t dims[3];
   int rc = 0;
-  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kCkptMagic, 8) != 0 || fread(&version, 4, 1, f) != 1 || version != 1 ||
-      fread(&cfg, sizeof(cfg), 1, f) != 1 || fread(dims, sizeof(dims), 1, f) != 1)
-    rc = set_error(CDAE_E_INVALID, "%s is not a cdae_b200 checkpoint (version 1)", path);
-  else if (dims[0] != h->U || dims[1] != h->I || dims[2] != h->K || cfg.asymmetric != h->cfg.asymmetric ||
-           cfg.user_factor != h->cfg.user_factor || cfg.linear_function != h->cfg.linear_function)
+  ckpt_cfg_pack(h->cfg, hd, hi);
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kCkptMagic, 8) != 0 || fread(&version, 4, 1, f) != 1 || version != kCkptVersion ||
+      fread(cd, sizeof(cd), 1, f) != 1 || fread(ci, sizeof(ci), 1, f) != 1 || fread(dims, sizeof(dims), 1, f) != 1)
+    rc = set_error(CDAE_E_INVALID, "%s is not a cdae_b200 checkpoint (version %u)", path, kCkptVersion);
+  else if (dims[0] != h->U || dims[1] != h->I || dims[2] != h->K || ci[5] != hi[5] || ci[6] != hi[6] || ci[9] != hi[9])
     rc = set_error(CDAE_E_INVALID, "checkpoint shape %lld x %lld, K=%lld does not match the model (%lld x %lld, K=%d)",
                    (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)h->U, (long long)h->I, h->K);
   std::vector<double> buf;
@@ -243,6 +277,9 @@ int cdae_load(cdae_handle* h, const char* path) {
     rc = cdae_set_param(h, (int)hdr[0], buf.data(), n);
   }
   fclose(f);
+  if (rc == 0 && (memcmp(cd, hd, sizeof(cd)) != 0 || memcmp(ci, hi, sizeof(ci)) != 0))
+    set_error(0, "note: %s was written with different hyper-parameters (lambda %g lr %g q %g beta %g loss %d); the handle's stay in force",
+              path, cd[0], cd[1], cd[2], cd[3], ci[0]);
   return rc;
 }
 

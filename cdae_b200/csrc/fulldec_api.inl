@@ -28,12 +28,10 @@ static int fd_pick_split(int tiles, int units, int min_units, int sms, int max_s
 template <int KB, int LT, bool BOUT>
 static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb_half,
                            const CUtensorMap& mg, const fd::ScoreArgs& a, dim3 grid, bool cluster2) {
-  static bool attr_set = false;
   const size_t dyn = fd::score_smem(KB);
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the CURRENT device (several handles / devices per process)
     CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT, BOUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     CU(cudaFuncSetAttribute(fd::fd_score_kernel<KB, LT, BOUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
   }
   if (!cluster2) {
     fd::fd_score_kernel<KB, LT, BOUT, false><<<grid, 640, dyn, h->stream>>>(ma, mb, mg, a);
@@ -50,12 +48,10 @@ static int fd_launch_score(cdae_handle* h, const CUtensorMap& ma, const CUtensor
 }
 template <int KB, bool ITEMGRAD, bool BOUT>
 static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const fd::GemmArgs& a, dim3 grid) {
-  static bool attr_set = false;
   const size_t dyn = fd::gemm_smem(KB);
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the CURRENT device (several handles / devices per process)
     CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     CU(cudaFuncSetAttribute(fd::fd_gemm_kernel<KB, ITEMGRAD, BOUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
   }
   // CDAE_B200_FD_GEMM_CLUSTER=1: pairs of output tiles share the B stream (Wb / Zb slabs of each
   // contraction step) through 2-CTA clusters with multicast TMA.  Parity-identical, measured neutral
@@ -79,12 +75,10 @@ static int fd_launch_gemm(cdae_handle* h, const CUtensorMap& ma, const CUtensorM
 template <int KB, int LT>
 static int fd_launch_fused(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw_half,
                            const CUtensorMap& mg, const fd::FusedArgs& a, dim3 grid, bool cluster2) {
-  static bool attr_set = false;
   const size_t dyn = fd::fused_smem(KB);
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the CURRENT device (several handles / devices per process)
     CU(cudaFuncSetAttribute(fd::fd_fused_kernel<KB, LT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     CU(cudaFuncSetAttribute(fd::fd_fused_kernel<KB, LT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
   }
   if (!cluster2) {
     fd::fd_fused_kernel<KB, LT, false><<<grid, 640, dyn, h->stream>>>(ma, mw, mg, a);

@@ -66,7 +66,10 @@ struct cdae_handle {
   cdae::DevBuf<cdae::WorkItem> plan_in, plan_out;
   cdae::DevBuf<int32_t> plan_uids;
   int64_t plan_max_slots = 0, plan_max_users = 0;
+  size_t plan_n_uids = 0;        // users this rank trains per epoch (length of plan_uids)
   bool plan_valid = false;
+  bool csr_bad = false;          // ... and failed: training calls are refused until a valid CSR arrives
+  bool csr_unchecked = false;    // the device CSR came from cdae_train_epoch_csr and has not been validated yet
   // explicit-user calls
   cdae::DevBuf<cdae::WorkItem> tmp_in, tmp_out;
   cdae::DevBuf<int32_t> tmp_uids;

@@ -57,11 +57,9 @@ static bool tc_path_wanted(cdae_handle* h, int topk) {
 template <int KB>
 static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, const tc::TcArgs& a, int grid_x) {
   const dim3 grid(grid_x, a.n_splits);
-  static bool attr_set = false;
   const size_t dyn = tc::smem_bytes(KB);
-  if (!attr_set) {
+  {  // per launch: the attribute belongs to the CURRENT device (several handles / devices per process)
     CU(cudaFuncSetAttribute(tc::topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
   }
   tc::topn_tc_kernel<KB><<<grid, tc::n_threads(KB), dyn, h->stream>>>(ma, mb, a);
   return 0;
@@ -287,6 +285,8 @@ int cdae_topn_evaluate(cdae_handle* h, const int64_t* trp, const int32_t* tcol, 
   if (h->world > 1) return set_error(CDAE_E_STATE, "evaluate per rank with cdae_topn_fetch in a process group");
   CU(cudaSetDevice(h->cfg.device));
   const int64_t nnz = trp[h->U];
+  if (nnz > 0 && !tcol) return set_error(CDAE_E_INVALID, "test_col is NULL");
+  TRY(validate_csr(h->U, h->I, trp, tcol));  // topn_metrics_kernel binary-searches the test rows
   TRY(ensure(h, h->test_rp_d, (size_t)h->U + 1));
   TRY(ensure(h, h->test_col_d, (size_t)std::max<int64_t>(nnz, 1)));
   TRY(ensure(h, h->stage_d, 9));

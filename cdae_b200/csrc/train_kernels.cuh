@@ -73,7 +73,7 @@ struct StatsDev {
   unsigned long long inputs_kept[STAT_STRIPES];
   unsigned long long user_steps;
   int bad_loss;  // LOGISTIC fed a score outside (0,1)
-  int pad;
+  int bad_csr;   // validate_rows_kernel found an item id out of range or an unsorted row
 };
 
 template <int G, int NV>
@@ -120,6 +120,37 @@ __device__ __forceinline__ bool row_contains(const int32_t* row, int n, int item
     if (__ldg(row + mid) < item) lo = mid + 1; else hi = mid;
   }
   return lo < n && __ldg(row + lo) == item;
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-side check of a CSR that arrived through cdae_train_epoch_csr (one warp per trained user):
+// item ids must lie in [0, I) and rows must be strictly ascending (the negative sampler and the
+// top-N exclusion binary-search them).  Out-of-range ids are clamped in the device copy, so that no
+// later kernel of the call can index outside a table; any violation sets stats->bad_csr (read by the
+// host after the call) and *flag (part of the all-reduced gradient buffer: every rank of a process
+// group sees it), which turn hidden_backward / uu_update / apply into no-ops.
+__global__ void __launch_bounds__(256) validate_rows_kernel(const int32_t* uids, int64_t n_users,
+                                                            const int64_t* row_ptr, int32_t* col, int64_t I,
+                                                            StatsDev* stats, float* flag) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_users) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t uid = uids[w];
+  const int64_t s0 = row_ptr[uid], s1 = row_ptr[uid + 1];
+  bool bad = false;
+  for (int64_t s = s0 + lane; s < s1; s += 32) {
+    const int32_t c = col[s];
+    if (c < 0 || (int64_t)c >= I) {
+      bad = true;
+      col[s] = 0;
+    } else if (s > s0 && col[s - 1] >= c) {
+      bad = true;
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) {
+    stats->bad_csr = 1;
+    red_add_f32(flag, 1.f);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -398,6 +429,7 @@ __global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchD
   const int c4 = threadIdx.x;  // < ld4n
   const int u = blockIdx.x * blockDim.y + threadIdx.y;
   float4 d = f4zero();
+  if (stats->bad_csr) return;  // invalid CSR (validate_rows_kernel): leave Wu untouched
   if (u < bt.n_users && c4 < ld4n) {
     const int c = c4 * 4;
     const float4 zz = ld4(bt.Z + (int64_t)u * m.ld + c);
@@ -517,9 +549,9 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 }
 
 // cdae.hpp:295-299,351-357: Uu[u] takes upd(lambda*Uu[u] + GU[u]) (linear_function only).
-__global__ void __launch_bounds__(256) uu_update_kernel(ModelDev m, BatchDev bt) {
+__global__ void __launch_bounds__(256) uu_update_kernel(ModelDev m, BatchDev bt, const StatsDev* stats) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)bt.n_users * m.ld) return;
+  if (idx >= (int64_t)bt.n_users * m.ld || stats->bad_csr) return;
   const int u = (int)(idx / m.ld), c = (int)(idx % m.ld);
   const int64_t uid = bt.uids[u];
   float* wp = m.Uu + uid * m.ld + c;
@@ -553,14 +585,20 @@ struct ApplyArgs {
   int nseg;
   float lr, beta;
   int adagrad;
-  float* g_steps;  // [2]: read slot `steps_slot`, clear the other one for the next minibatch
+  float* g_steps;  // [0..1]: read slot `steps_slot`, clear the other one for the next minibatch;
+                   // [2] != 0: some rank's CSR failed validate_rows_kernel -> discard the gradients
   int steps_slot;
   float* cnt_clear;  // the occurrence counters of the OTHER slot (consumed by the previous apply)
   int64_t n_cnt;
+  int* bad_csr_out;  // StatsDev::bad_csr: raised when the gradients were discarded (another rank's CSR was invalid)
 };
 __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
   const float steps = a.g_steps[a.steps_slot];
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.g_steps[a.steps_slot ^ 1] = 0.f;
+  const bool discard = a.g_steps[2] != 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.g_steps[a.steps_slot ^ 1] = 0.f;
+    if (discard) *a.bad_csr_out = 1;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_cnt / 4; i += (int64_t)gridDim.x * blockDim.x)
     st4(a.cnt_clear + i * 4, f4zero());
   for (int s = 0; s < a.nseg; ++s) {
@@ -571,6 +609,10 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
       float4 g4 = ld4(sg.g + i * 4);
       const float rowc = sg.cnt ? sg.cnt_coef * __ldg(sg.cnt + i / sg.ld4) : 0.f;
       if (extra == 0.f && rowc == 0.f && g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) continue;
+      if (discard) {
+        st4(sg.g + i * 4, f4zero());
+        continue;
+      }
       float4 w4 = ld4(sg.w + i * 4);
       float g[4] = {g4.x, g4.y, g4.z, g4.w};
       float w[4] = {w4.x, w4.y, w4.z, w4.w};

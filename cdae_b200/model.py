@@ -150,7 +150,9 @@ class CDAE:
         if csr is None:
             _lib.check(self._L.cdae_train_epoch(self._h, seed, epoch, C.byref(st)))
         else:
-            rp, cl = csr
+            rp, cl = _arr(csr[0], np.int64), _arr(csr[1], np.int32)   # no copy when already int64 / int32
+            if len(rp) != self.U + 1 or len(cl) < rp[-1]:
+                raise CdaeError(-1, "csr must be (row_ptr[U+1] int64, col[nnz] int32)")
             _lib.check(self._L.cdae_train_epoch_csr(self._h, _ptr(rp, _lib.i64p), _ptr(cl, _lib.i32p),
                                                     seed, epoch, C.byref(st)))
         self.last_stats = st
@@ -296,6 +298,12 @@ class CDAE:
         cnt = (C.c_int64 * n)()
         _lib.check(self._L.cdae_profile_get(self._h, ms, cnt))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
+    def probe_l2(self, rows, mode, row_visits, reps=20):
+        """(GB/s, ms per launch) of the L2 row-load (mode 1) / row-reduction (2) / both (3) pattern."""
+        g, ms = C.c_double(), C.c_double()
+        _lib.check(self._L.cdae_probe_l2(self._h, rows, mode, row_visits, reps, C.byref(g), C.byref(ms)))
+        return g.value, ms.value
 
     def pinned_array(self, src):
         """Copy of `src` in pinned host memory (cdae_host_alloc); freed with the model."""

@@ -26,11 +26,18 @@ def _draw_lengths(rng, U, I, mean):
     return np.clip(n, min(10, hi), hi)
 
 
-def make_dataset(U, I, mean_train=30.0, seed=DEFAULT_SEED, test_ratio=0.2, alpha=1.0):
-    """Returns dict(train_row_ptr, train_col, test_row_ptr, test_col, U, I)."""
+def make_dataset(U, I, mean_train=30.0, seed=DEFAULT_SEED, test_ratio=0.2, alpha=1.0, item_seed=None):
+    """Returns dict(train_row_ptr, train_col, test_row_ptr, test_col, U, I).
+
+    ``item_seed`` (optional) draws the popularity permutation of the items from its own stream, so
+    that blocks of users generated with different ``seed`` share ONE item popularity model
+    (make_sharded_dataset)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_full = _draw_lengths(rng, U, I, mean_train / (1.0 - test_ratio))
-    perm = rng.permutation(I).astype(np.int64)            # popularity rank -> item id
+    if item_seed is None:
+        perm = rng.permutation(I).astype(np.int64)        # popularity rank -> item id
+    else:
+        perm = np.random.Generator(np.random.PCG64(item_seed)).permutation(I).astype(np.int64)
     w = 1.0 / np.power(np.arange(1, I + 1, dtype=np.float64), alpha)
     cdf = np.cumsum(w)
     cdf /= cdf[-1]
@@ -97,3 +104,52 @@ def make_params(U, I, K, seed=DEFAULT_SEED, asymmetric=False, user_factor=True):
     if user_factor:
         p["Wu"] = (rng.uniform(-1, 1, (U, K)) * s).astype(np.float32).astype(np.float64)
     return p
+
+
+def owned_users(U, batch_users, rank, world):
+    """Global ids of the users rank `rank` trains: its contiguous slice of every global minibatch of
+    `batch_users` users — the rule of build_plan (csrc/api.cu) and cdae_b200/dist.py."""
+    out = []
+    for lo in range(0, U, batch_users):
+        n = min(batch_users, U - lo)
+        out.append(np.arange(lo + n * rank // world, lo + n * (rank + 1) // world, dtype=np.int64))
+    return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+
+def make_sharded_dataset(U, I, mean_train, batch_users, rank, world, seed=DEFAULT_SEED):
+    """The part of a U x I data set that ONE rank of a data-parallel group needs ("each
+    GPU holds its CSR shard"): the rows of the users it owns, generated as an independent block
+    (seed + rank) over the shared item popularity model (item_seed = seed).  Returned as a GLOBAL
+    CSR in which the rows of users owned by other ranks are empty, which is what cdae_create /
+    cdae_train_epoch_csr take in a process group (they only ever read the rows a rank trains).
+    world == 1 is make_dataset(U, I, mean_train, seed) with the shared item stream."""
+    own = owned_users(U, batch_users, rank, world)
+    d = make_dataset(len(own), I, mean_train, seed=seed + rank, item_seed=seed)
+    out = dict(U=U, I=I, owned=own)
+    for part in ("train", "test"):
+        lens = np.zeros(U, np.int64)
+        lens[own] = np.diff(d[part + "_row_ptr"])
+        out[part + "_row_ptr"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out[part + "_col"] = d[part + "_col"]            # owned users ascend with their local index
+    return out
+
+
+def make_blocked_dataset(U, I, mean_train, seed=DEFAULT_SEED, block_users=16384, workers=None):
+    """make_dataset for large U: blocks of `block_users` users generated independently (seed + block
+    index) over one shared item popularity model and concatenated; blocks run on a thread pool (numpy's
+    sort / unique release the GIL).  The cost of make_dataset is dominated by sorting all (user, item)
+    keys at once, so this is several times faster at config C / D sizes and gives the same
+    distribution (not the same arrays) as one call."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nb = (U + block_users - 1) // block_users
+    sizes = [min(block_users, U - b * block_users) for b in range(nb)]
+    workers = workers or min(nb, os.cpu_count() or 1, 32)
+    with ThreadPoolExecutor(workers) as ex:
+        parts = list(ex.map(lambda b: make_dataset(sizes[b], I, mean_train, seed=seed + b, item_seed=seed), range(nb)))
+    out = dict(U=U, I=I)
+    for part in ("train", "test"):
+        lens = np.concatenate([np.diff(p[part + "_row_ptr"]) for p in parts])
+        out[part + "_row_ptr"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out[part + "_col"] = np.concatenate([p[part + "_col"] for p in parts])
+    return out

@@ -141,7 +141,11 @@ int cdae_train_epoch(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_st
 /* Same, with the training CSR taken from HOST memory on every call, the way
  * train_one_iteration(const Data&) receives its data each epoch.  Shapes must match
  * cdae_create (same U; nnz may differ).  H2D copy and the D2H read of stats are inside
- * the call. */
+ * the call.  row_ptr is checked on the host when it changed; col is checked ON THE DEVICE after the
+ * upload (ids in [0, I), rows strictly ascending; in a process group each rank checks the rows it
+ * trains): a violation returns CDAE_E_INVALID with no parameter updated (out-of-range ids are clamped
+ * in the device copy, so no kernel indexes outside a table), and training calls are refused until a
+ * valid CSR is passed. */
 int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* col_idx,
                          uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats);
 
@@ -208,8 +212,11 @@ int cdae_dataset_free(cdae_dataset* d);
 
 /* Model checkpoint (the reference has none — its save/load only cover Data):
  * versioned binary file with the config, the shape and every parameter block incl. AdaGrad state
- * as doubles.  cdae_load needs a handle created with the same shape and the same structural
- * options (asymmetric, user_factor, linear_function).  Single-process. */
+ * as doubles; the config is stored field by field at fixed widths.  cdae_load needs a handle created
+ * with the same shape and the same structural options (asymmetric, user_factor, linear_function); the
+ * handle's other hyper-parameters stay in force (a difference is noted in cdae_last_error(), rc 0).
+ * In a process group cdae_save is COLLECTIVE (user-private blocks are assembled from their owning
+ * ranks): every rank calls it, only rank 0 writes `path`; every rank calls cdae_load on the same file. */
 int cdae_save(cdae_handle* h, const char* path);
 int cdae_load(cdae_handle* h, const char* path);
 
@@ -243,6 +250,15 @@ enum cdae_kernel_class {
 int cdae_profile(cdae_handle* h, int32_t enable);
 int cdae_profile_get(cdae_handle* h, double* ms_out /*[CDAE_K_COUNT]*/,
                      int64_t* launches_out /*[CDAE_K_COUNT]*/);
+
+/* Measurement aid (no reference counterpart): the L2 roofline of the sampled decode's access pattern.
+ * When the item tables and their gradients fit the 126 MB L2 (config B: 38 MB) the decode kernel is
+ * bound by L2 transactions, not HBM.  This runs a kernel that issues only those transactions —
+ * `row_visits` uniformly random rows of a `rows` x ld fp32 table, 16-byte vector loads (mode & 1)
+ * and / or 16-byte vector reductions into a second table (mode & 2), in the handle's row geometry —
+ * and returns bytes moved per second (GB/s) and the average launch time over `reps` launches. */
+int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits, int32_t reps,
+                  double* gbs_out, double* ms_out);
 
 /* pinned host memory for buffers that cross the boundary every step */
 int cdae_host_alloc(void** ptr, int64_t bytes);

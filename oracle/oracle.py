@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "libcdae_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libcdae_ref.so")
+REF_V3_SO = os.path.join(HERE, "_ref", "libcdae_ref_v3.so")   # same sources, -march=x86-64-v3 (bench baseline only)
 
 LOSS = {"SQUARE": 0, "LOGISTIC": 1, "LOG": 2, "HINGE": 3, "SQUARED_HINGE": 4, "CE": 5,
         "CROSS_ENTROPY": 5, "LOGM": 6}
@@ -33,7 +34,7 @@ def build(ref=True):
     """Compile the checker (and, where /root/reference exists, the reference driver)."""
     subprocess.check_call(["make", "-s", "-C", HERE, "all"])
     if ref and os.path.isdir("/root/reference/src/model/recsys"):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "ref_v3"])
 
 
 def default_config(**kw):
@@ -318,17 +319,28 @@ class Oracle:
         return self._L.orc_train_epoch_hogwild(self._h, seed, epoch, u0, u1, n_threads)
 
 
-_ref_lib = None
+_ref_libs = {}
 
 
 def have_reference():
     return os.path.exists(REF_SO)
 
 
-def _ref():
-    global _ref_lib
+def _ref(so=None):
+    """The reference driver library (default build, or another build of the same sources)."""
+    so = so or REF_SO
+    if so not in _ref_libs:
+        _ref_libs[so] = _ref_load(so)
+    return _ref_libs[so]
+
+
+_ref_libs = {}
+
+
+def _ref_load(path):
+    _ref_lib = None
     if _ref_lib is None:
-        L = C.CDLL(REF_SO)
+        L = C.CDLL(path)
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [f64p, i32p, C.c_char_p]
         L.ref_destroy.argtypes = [C.c_void_p]
@@ -401,12 +413,12 @@ class Reference:
     with the oracle's; use ``first_seen_relabel`` to build such a CSR.
     """
 
-    def __init__(self, cfg, U, I, row_ptr, col, quiet=True):
+    def __init__(self, cfg, U, I, row_ptr, col, quiet=True, so=None):
         if quiet:
             os.environ.setdefault("GLOG_minloglevel", "1")
         self.cfg = dict(cfg)
         self.U, self.I, self.K = int(U), int(I), int(cfg["num_dim"])
-        self._L = _ref()
+        self._L = _ref(so)
         d = _as([cfg["lambda_"], cfg["learn_rate"], cfg["corruption_ratio"], cfg["beta"]], np.float64)
         i = _as([LOSS[cfg["loss"]], cfg["num_dim"], cfg["num_neg"], cfg["num_corruptions"],
                  cfg["using_adagrad"], cfg["asymmetric"], cfg["user_factor"], cfg["linear"],
@@ -427,8 +439,8 @@ class Reference:
             self._h = None
 
     @staticmethod
-    def seed(mt_seed, c_seed):
-        _ref().ref_seed(mt_seed, c_seed)
+    def seed(mt_seed, c_seed, so=None):
+        _ref(so).ref_seed(mt_seed, c_seed)
 
     def shape(self, name):
         r, c = C.c_int64(), C.c_int64()

@@ -97,4 +97,6 @@ CONFIG_GRID = [
     dict(num_neg=1, num_dim=50),
     dict(num_neg=0),
     dict(loss="LOG"), dict(loss="HINGE"), dict(loss="SQUARED_HINGE"), dict(loss="LOGM"),
+    dict(corruption_ratio=1.0, beta=1.0),       # q = 1 with scaled: 1/(1-q) = inf is never multiplied (cdae.hpp:366,377-380)
+    dict(corruption_ratio=1.0, scaled=False, asymmetric=True),
 ]

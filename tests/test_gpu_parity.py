@@ -110,7 +110,8 @@ def test_frozen_minibatch_matches_oracle(orc, kw):
 @pytest.mark.parametrize("kw", [dict(loss="CE", beta=1.0), dict(loss="SQUARE", asymmetric=True),
                                 dict(loss="CE", num_corruptions=2, corruption_ratio=0.3),
                                 dict(loss="CE", corruption_ratio=0.0, scaled=False),
-                                dict(loss="CE", corruption_ratio=1.0, scaled=False)])
+                                dict(loss="CE", corruption_ratio=1.0, scaled=False),
+                                dict(loss="CE", corruption_ratio=1.0, beta=1.0)])   # q = 1 AND scaled: no inf * 0
 def test_epoch_with_device_sampling_matches_oracle(orc, kw):
     """cdae_train_epoch: Philox masks/negatives on the device == the same streams on the CPU."""
     cfg = orc.default_config(**kw)
@@ -313,3 +314,95 @@ def test_checkpoint_round_trip(orc, tmp_path):
                    U, I, rp, col, {})
     with pytest.raises(CdaeError):
         m3.load(path)
+
+
+def test_q1_scaled_losses_are_finite(orc):
+    """q == 1 with scaled made scale = inf and every hidden value NaN."""
+    cfg = orc.default_config(loss="CE", corruption_ratio=1.0, beta=1.0)
+    data = cases.small_dataset(U=64, I=200, mean=10.0, seed=4)
+    U, I = data["U"], data["I"]
+    rp, col = data["train_row_ptr"], data["train_col"]
+    p = cases.random_params(U, I, cfg["num_dim"], 3, False, True)
+    o = orc.Oracle(cfg, U, I, rp, col)
+    o.set_params(p)
+    m = gpu_model(cfg, U, I, rp, col, p)
+    dl = m.data_loss(seed=1)
+    assert np.isfinite(dl)
+    assert abs(dl - o.data_loss(np.zeros(len(col), np.uint8))) <= 1e-4 * abs(dl)
+    ids, _ = m.recommend_all(10)           # cdae.hpp:168: the input set is empty when q == 1
+    for u in range(U):
+        assert ids[u].tolist() == o.recommend(u, 10)[0].tolist()
+
+
+def test_train_epoch_csr_rejects_a_bad_csr_without_touching_parameters(orc):
+    """the host-CSR call must not index tables with unchecked ids.  The column array is
+    checked on the device; a violation is an error, the parameters stay as they were, and training is
+    refused until a valid CSR arrives."""
+    from cdae_b200 import CdaeError
+    cfg = orc.default_config(loss="CE", beta=1.0)
+    data = cases.small_dataset(U=150, I=300, mean=10.0, seed=6)
+    U, I = data["U"], data["I"]
+    rp, col = data["train_row_ptr"], data["train_col"]
+    p = cases.random_params(U, I, cfg["num_dim"], 3, False, True)
+    for kind in ("range", "negative", "unsorted"):
+        m = gpu_model(cfg, U, I, rp, col, p, batch_users=64)
+        before = m.get_params()
+        bad = col.copy()
+        s = int(rp[70]) + 1
+        if kind == "range":
+            bad[s] = I + 12345
+        elif kind == "negative":
+            bad[s] = -7
+        else:
+            bad[s - 1], bad[s] = bad[s], bad[s - 1]
+        with pytest.raises(CdaeError):
+            m.train_one_iteration(seed=3, epoch=0, csr=(rp, bad))
+        after = m.get_params()
+        for k in before:
+            assert np.array_equal(before[k], after[k]), (kind, k)
+        with pytest.raises(CdaeError):
+            m.train_one_iteration(seed=3, epoch=0)                       # resident CSR is known bad
+        # a valid CSR heals the handle and trains exactly like a fresh one
+        m.train_one_iteration(seed=3, epoch=0, csr=(rp, col))
+        m2 = gpu_model(cfg, U, I, rp, col, p, batch_users=64)
+        m2.train_one_iteration(seed=3, epoch=0)
+        for k in ("W", "b", "b_prime", "Wu"):
+            np.testing.assert_allclose(m.get_param(k), m2.get_param(k), rtol=1e-5, atol=1e-6, err_msg=kind + " " + k)
+    # dtype coercion in the Python mirror: an int32 row_ptr is converted, not reinterpreted
+    m = gpu_model(cfg, U, I, rp, col, p, batch_users=64)
+    m.train_one_iteration(seed=3, epoch=0, csr=(rp.astype(np.int32), col.astype(np.int64)))
+
+
+def test_c_abi_refuses_stale_recommendations(orc):
+    """cdae_topn_lookup / fetch / evaluate must not serve lists built before a parameter
+    update — checked at the C ABI, below the wrappers' own bookkeeping."""
+    import ctypes as C
+    from cdae_b200 import _lib
+    cfg = orc.default_config(loss="CE", beta=1.0)
+    data = cases.small_dataset(U=64, I=200, mean=10.0, seed=8)
+    U, I = data["U"], data["I"]
+    rp, col = data["train_row_ptr"], data["train_col"]
+    p = cases.random_params(U, I, cfg["num_dim"], 3, False, True)
+    m = gpu_model(cfg, U, I, rp, col, p)
+    L = _lib.lib()
+    ids = np.zeros(10, np.int64)
+
+    def lookup():
+        return L.cdae_topn_lookup(m._h, 3, ids.ctypes.data_as(_lib.i64p), None)
+
+    assert L.cdae_topn_build(m._h, 10) == 0 and lookup() == 0
+    m.train_one_iteration(seed=1, epoch=0)
+    assert lookup() == -4                                                # CDAE_E_STATE
+    assert L.cdae_topn_build(m._h, 10) == 0 and lookup() == 0
+    m.set_params({"b": p["b"]})
+    assert lookup() == -4
+    assert L.cdae_topn_build(m._h, 10) == 0 and lookup() == 0
+    m.init_params(5)
+    assert lookup() == -4
+    # unsorted test rows are refused by cdae_topn_evaluate (it binary-searches them)
+    assert L.cdae_topn_build(m._h, 10) == 0
+    trp, tcol = data["test_row_ptr"], data["test_col"].copy()
+    u = int(np.argmax(np.diff(trp) >= 2))
+    tcol[trp[u]], tcol[trp[u] + 1] = tcol[trp[u] + 1], tcol[trp[u]]
+    with pytest.raises(_lib.CdaeError):
+        m.topn_evaluate(trp, tcol)
