@@ -410,7 +410,7 @@ def measure(name, ctx, args, primary):
         res["kernel_share_note"] = ("from a separate profiled pass (event pair around every launch, %.3f ms per step against "
                                     "%.3f unprofiled)" % (prof_ms / steps, dev_ms / steps))
         if c["full"]:
-            res["roofline"] = tensor_roofline(c, prof, steps, users_all / world, dev_ms / steps, pk)
+            res["roofline"] = tensor_roofline(c, prof, steps, users_all / world / steps, dev_ms / steps, pk)
         else:
             res["roofline"] = decode_roofline(m, c, prof, prof_out, pk)
     ctx.last_model = m
@@ -464,7 +464,8 @@ def decode_roofline(m, c, prof, outputs_profiled, pk):
 
 def tensor_roofline(c, prof, steps, users_rank, step_ms, pk):
     """Full-item decode: the three tcgen05 contractions, 6*I*K flops per user, against the
-    SUSTAINED bf16 peak (the kernels run back to back inside a long step)."""
+    SUSTAINED bf16 peak (the kernels run back to back inside a long step).  users_rank = users one rank
+    trains per epoch."""
     per = {k: v[0] / steps for k, v in prof.items() if v[1]}
     tens = [k for k in ("fd_score", "fd_hidden", "fd_itemgrad") if k in per]
     tens_ms = sum(per[k] for k in tens)

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libcdae_b200.so")
+SO = os.environ.get("CDAE_B200_LIB") or os.path.join(HERE, "libcdae_b200.so")   # the override is for A/B builds of the same sources
 
 LOSS = {"SQUARE": 0, "LOGISTIC": 1, "LOG": 2, "HINGE": 3, "SQUARED_HINGE": 4, "CE": 5,
         "CROSS_ENTROPY": 5, "LOGM": 6}

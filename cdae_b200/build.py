@@ -23,7 +23,14 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    """out: build a variant library elsewhere (A/B runs: CDAE_NVCC_FLAGS='-DDECODE_UNR=2' and
+    CDAE_B200_LIB=<that path> at run time)."""
+    if out:
+        nvcc = os.environ.get("NVCC", "nvcc")
+        extra = os.environ.get("CDAE_NVCC_FLAGS", "").split()
+        subprocess.check_call([nvcc] + NVCC_FLAGS + extra + SOURCES + ["-o", out, "-ldl"])
+        return out
     if not force and up_to_date():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")

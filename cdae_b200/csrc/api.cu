@@ -87,7 +87,7 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
-const int kNcclFloat = 7, kNcclSum = 0;
+const int kNcclFloat = 7, kNcclDouble = 8, kNcclSum = 0;
 
 int load_nccl() {
   if (g_nccl.lib) return 0;
@@ -145,14 +145,37 @@ static float* param_ptr(cdae_handle* h, int which, int64_t* rows, int64_t* cols,
   return p;
 }
 
-static int alloc_table(cdae_handle* h, float** p, int64_t rows, int K, int ld, float fill) {
-  CU(cudaMalloc(p, sizeof(float) * (size_t)std::max<int64_t>(rows * ld, 4)));
-  h->dev_bytes += sizeof(float) * (size_t)(rows * ld);
+static int fill_table(cdae_handle* h, float* p, int64_t rows, int K, int ld, float fill) {
   if (rows * ld > 0) {
-    fill_kernel<<<cdiv(rows * ld, 256), 256, 0, h->stream>>>(*p, rows, K, ld, fill);
+    fill_kernel<<<cdiv(rows * ld, 256), 256, 0, h->stream>>>(p, rows, K, ld, fill);
     KERNEL_OK(h);
   }
   return 0;
+}
+static int alloc_table(cdae_handle* h, float** p, int64_t rows, int K, int ld, float fill) {
+  CU(cudaMalloc(p, sizeof(float) * (size_t)std::max<int64_t>(rows * ld, 4)));
+  h->dev_bytes += sizeof(float) * (size_t)(rows * ld);
+  return fill_table(h, *p, rows, K, ld, fill);
+}
+
+// The item side lives in THREE flat buffers of one layout, [W | V (asymmetric) | b' | counts x2 | b | steps]:
+// parameters, AdaGrad state, and the per-minibatch gradients (the counts / steps slots exist only in the
+// gradient buffer; they are padding in the other two).  Element i of the gradient buffer is the
+// gradient of element i of the parameter buffer, so the optimiser step — and its slice-per-rank form
+// over NVLink peer memory (p2p_allreduce.cuh) — is one flat elementwise pass.
+static void point_item_side(cdae_handle* h, float* grad_base) {
+  ModelDev& m = h->m;
+  const int64_t I = h->I;
+  const bool asym = h->cfg.asymmetric != 0;
+  float *p = h->item_params.p, *a = h->item_acc.p, *g = grad_base;
+  size_t off = 0;
+  m.W = p + off; m.W_ag = a + off; m.gW = g + off; off += (size_t)(I * h->ld);
+  if (asym) { m.V = p + off; m.V_ag = a + off; m.gV = g + off; off += (size_t)(I * h->ld); }
+  else { m.V = nullptr; m.V_ag = nullptr; m.gV = nullptr; }
+  m.bp = p + off; m.bp_ag = a + off; m.gbp = g + off; off += (size_t)h->I4;
+  m.gcnt = g + off; off += 2 * (size_t)h->I4;
+  m.b = p + off; m.b_ag = a + off; m.gb = g + off; off += (size_t)h->ld;
+  m.g_steps = g + off;
 }
 
 template <class T>
@@ -391,6 +414,7 @@ static SampleArgs make_sample_args(cdae_handle* h, uint64_t seed, uint32_t pass)
 }
 
 static int run_fulldec(cdae_handle* h, const BatchDev& bt);   // fulldec_api.inl
+static int combine_and_apply(cdae_handle* h);
 
 // gather -> activate -> decode -> hidden_backward -> scatter -> [all-reduce] -> apply
 static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleArgs* sa) {
@@ -425,11 +449,55 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleA
     uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt, h->stats_d);
     KERNEL_OK(h);
   }
+  TRY(combine_and_apply(h));
+  return 0;
+}
+
+// The end of a minibatch: item-side gradients of all ranks are combined and upd() is applied once.
+//   single GPU                : apply_kernel
+//   process group, peer memory: p2p::fused_step_kernel — reduce-scatter by peer loads, the rank's slice of
+//                               the optimiser step, all-gather of the updated parameters by peer stores
+//   process group, NCCL       : ncclAllReduce of the gradient buffer, then apply_kernel on every rank
+static int combine_and_apply(cdae_handle* h) {
   // CDAE_B200_DEBUG_SKIP_ALLREDUCE=1: measurement aid only (ranks diverge) — isolates the cost of
   // the collective in a scaling run
   static const bool skip_allreduce = getenv("CDAE_B200_DEBUG_SKIP_ALLREDUCE") != nullptr;
+  if (h->world > 1 && !skip_allreduce && h->p2p_on && h->p2p_fused) {
+    ProfScope ps(h, CDAE_K_ALLREDUCE);
+    p2p::FusedArgs fa;
+    const size_t cur = (size_t)h->p2p_parity * h->grad_floats, nxt = (size_t)(h->p2p_parity ^ 1) * h->grad_floats;
+    for (int r = 0; r < p2p::MAX_RANKS; ++r) {
+      fa.grads[r] = h->p2p_bufs[r] ? h->p2p_bufs[r] + cur : nullptr;
+      fa.params[r] = h->p2p_params[r];
+      fa.flags[r] = h->p2p_flags[r];
+    }
+    fa.acc = h->item_acc.p;
+    fa.grad_next = h->grad.p + nxt;
+    fa.done = h->p2p_done;
+    fa.bad_csr_out = &h->stats_d->bad_csr;
+    fa.rank = h->rank; fa.world = h->world;
+    h->p2p_epoch += 2;
+    fa.epoch = h->p2p_epoch - 1;                    // the kernel announces epoch (gradients complete) and epoch + 1 (stores out)
+    fa.n4 = (int64_t)(h->grad_floats / 4);
+    const int64_t ld4 = h->ld / 4, rows4 = h->I * ld4;
+    fa.w_rows_end = rows4;
+    fa.w_end = rows4 * (h->m.asym ? 2 : 1);
+    fa.bp_end = fa.w_end + h->I4 / 4;
+    fa.b_lo = fa.bp_end + 2 * (h->I4 / 4);
+    fa.b_hi = fa.b_lo + ld4;
+    fa.ld4 = (int)ld4;
+    fa.cnt_off = (int64_t)(h->m.gcnt - h->m.gW);     // slot 0 (the whole buffer is cleared every other minibatch)
+    fa.steps_off = (int64_t)(h->m.g_steps - h->m.gW);
+    fa.steps_slot = 0;
+    fa.lr = h->m.lr; fa.beta = h->m.beta; fa.lambda = h->m.lambda; fa.adagrad = h->m.adagrad;
+    p2p::fused_step_kernel<<<h->sm_count, 512, 0, h->stream>>>(fa);
+    KERNEL_OK(h);
+    h->p2p_parity ^= 1;
+    point_item_side(h, h->grad.p + (size_t)h->p2p_parity * h->grad_floats);
+    return 0;
+  }
   if (h->world > 1 && !skip_allreduce && h->p2p_on) {
-    // two-shot all-reduce over NVLink peer memory (p2p_allreduce.cuh) + the barrier before apply
+    // two-shot all-reduce over NVLink peer memory + the barrier before the replicated apply
     ProfScope ps(h, CDAE_K_ALLREDUCE);
     p2p::Args pa;
     for (int r = 0; r < p2p::MAX_RANKS; ++r) { pa.bufs[r] = h->p2p_bufs[r]; pa.flags[r] = h->p2p_flags[r]; }
@@ -586,12 +654,21 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   int rc = 0;
   do {
     // cdae.hpp:109-134: accumulators 1e-4, b = b' = 0, Uu = 1
-    if ((rc = alloc_table(h, &m.W, I, h->K, h->ld, 0.f))) break;
-    if ((rc = alloc_table(h, &m.W_ag, I, h->K, h->ld, 1e-4f))) break;
-    if (cfg->asymmetric) {
-      if ((rc = alloc_table(h, &m.V, I, h->K, h->ld, 0.f))) break;
-      if ((rc = alloc_table(h, &m.V_ag, I, h->K, h->ld, 1e-4f))) break;
-    }
+    // the item side: flat parameter / accumulator / gradient buffers of one layout (point_item_side)
+    h->grad_floats = (size_t)(I * h->ld) * (cfg->asymmetric ? 2 : 1) + 3 * (size_t)h->I4 + (size_t)h->ld + 4;
+    if ((rc = ensure(h, h->item_params, h->grad_floats))) break;
+    if ((rc = ensure(h, h->item_acc, h->grad_floats))) break;
+    if ((rc = ensure(h, h->grad, h->grad_floats))) break;
+    h->dev_bytes += 3 * sizeof(float) * h->grad_floats;
+    if (cudaMemsetAsync(h->item_params.p, 0, sizeof(float) * h->grad_floats, h->stream) != cudaSuccess ||
+        cudaMemsetAsync(h->item_acc.p, 0, sizeof(float) * h->grad_floats, h->stream) != cudaSuccess ||
+        cudaMemsetAsync(h->grad.p, 0, sizeof(float) * h->grad_floats, h->stream) != cudaSuccess) { rc = set_error(CDAE_E_CUDA, "memset"); break; }
+    m.I4 = h->I4;
+    point_item_side(h, h->grad.p);
+    if ((rc = fill_table(h, m.W_ag, I, h->K, h->ld, 1e-4f))) break;
+    if (cfg->asymmetric && (rc = fill_table(h, m.V_ag, I, h->K, h->ld, 1e-4f))) break;
+    if ((rc = fill_table(h, m.b_ag, 1, h->K, h->ld, 1e-4f))) break;
+    if ((rc = fill_table(h, m.bp_ag, 1, (int)I, (int)h->I4, 1e-4f))) break;
     if (cfg->user_factor) {
       if ((rc = alloc_table(h, &m.Wu, U, h->K, h->ld, 0.f))) break;
       if ((rc = alloc_table(h, &m.Wu_ag, U, h->K, h->ld, 1e-4f))) break;
@@ -600,22 +677,6 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
       if ((rc = alloc_table(h, &m.Uu, U, h->K, h->ld, 1.f))) break;
       if ((rc = alloc_table(h, &m.Uu_ag, U, h->K, h->ld, 1e-4f))) break;
     }
-    if ((rc = alloc_table(h, &m.b, 1, h->K, h->ld, 0.f))) break;
-    if ((rc = alloc_table(h, &m.b_ag, 1, h->K, h->ld, 1e-4f))) break;
-    if ((rc = alloc_table(h, &m.bp, 1, (int)I, (int)h->I4, 0.f))) break;
-    if ((rc = alloc_table(h, &m.bp_ag, 1, (int)I, (int)h->I4, 1e-4f))) break;
-    // one contiguous gradient buffer: [gW | gV | gb' | input-occurrence counts x2 | gb | steps]
-    h->grad_floats = (size_t)(I * h->ld) * (cfg->asymmetric ? 2 : 1) + 3 * (size_t)h->I4 + (size_t)h->ld + 4;
-    if ((rc = ensure(h, h->grad, h->grad_floats))) break;
-    if (cudaMemsetAsync(h->grad.p, 0, sizeof(float) * h->grad_floats, h->stream) != cudaSuccess) { rc = set_error(CDAE_E_CUDA, "memset"); break; }
-    float* g = h->grad.p;
-    m.gW = g; g += I * h->ld;
-    if (cfg->asymmetric) { m.gV = g; g += I * h->ld; }
-    m.gbp = g; g += h->I4;
-    m.gcnt = g; g += 2 * h->I4;
-    m.I4 = h->I4;
-    m.gb = g; g += h->ld;
-    m.g_steps = g;
     // CSR
     h->row_ptr_h.assign(row_ptr, row_ptr + U + 1);
     if ((rc = ensure(h, h->row_ptr_d, (size_t)U + 1))) break;
@@ -640,15 +701,17 @@ int cdae_destroy(cdae_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < 8 && h->p2p_ipc; ++r) {
     if (r == h->rank) continue;
     if (h->p2p_bufs[r]) cudaIpcCloseMemHandle(h->p2p_bufs[r]);
+    if (h->p2p_params[r]) cudaIpcCloseMemHandle(h->p2p_params[r]);
     if (h->p2p_flags[r]) cudaIpcCloseMemHandle(h->p2p_flags[r]);
   }
   if (h->p2p_my_flags) cudaFree(h->p2p_my_flags);
   ModelDev& m = h->m;
-  float* tabs[] = {m.W, m.V, m.Wu, m.b, m.bp, m.Uu, m.W_ag, m.V_ag, m.Wu_ag, m.b_ag, m.bp_ag, m.Uu_ag};
+  float* tabs[] = {m.Wu, m.Uu, m.Wu_ag, m.Uu_ag};
   for (float* p : tabs) if (p) cudaFree(p);
+  h->item_params.release(); h->item_acc.release();
   h->grad.release(); h->row_ptr_d.release(); h->col_d.release();
   h->plan_in.release(); h->plan_out.release(); h->plan_uids.release();
   h->tmp_in.release(); h->tmp_out.release(); h->tmp_uids.release();
@@ -739,6 +802,19 @@ int cdae_get_param(cdae_handle* h, int which, double* dst, int64_t n) {
     NC(g_nccl.AllReduce(h->stage_f.p, h->stage_f.p, (size_t)(r * ld), kNcclFloat, kNcclSum, (ncclComm_t)h->comm, h->stream));
     src = h->stage_f.p;
   }
+  const bool item_acc_block = which == CDAE_P_W_AG || which == CDAE_P_V_AG || which == CDAE_P_B_AG || which == CDAE_P_BPRIME_AG;
+  if (h->world > 1 && h->p2p_on && h->p2p_fused && item_acc_block) {
+    // fused peer-memory mode shards the AdaGrad state: rank q keeps elements [n*q/world, n*(q+1)/world) of the
+    // flat item-side buffer current.  Keep the owned part of the block, zero the rest, sum across ranks.
+    const int64_t nblk = vec_bp ? h->I4 : r * (int64_t)ld;
+    const int64_t n4 = (int64_t)(h->grad_floats / 4);
+    const int64_t lo = 4 * (n4 * h->rank / h->world), hi = 4 * (n4 * (h->rank + 1) / h->world);
+    TRY(ensure(h, h->stage_f, (size_t)nblk));
+    owned_flat_kernel<<<cdiv(nblk, 256), 256, 0, h->stream>>>(h->stage_f.p, p, nblk, (int64_t)(p - h->item_acc.p), lo, hi);
+    KERNEL_OK(h);
+    NC(g_nccl.AllReduce(h->stage_f.p, h->stage_f.p, (size_t)nblk, kNcclFloat, kNcclSum, (ncclComm_t)h->comm, h->stream));
+    src = h->stage_f.p;
+  }
   unpack_to_double_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(h->stage_d.p, src, r, K, L);
   KERNEL_OK(h);
   CU(cudaMemcpyAsync(dst, h->stage_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -747,6 +823,18 @@ int cdae_get_param(cdae_handle* h, int which, double* dst, int64_t n) {
 }
 
 // selected rows of a table (or selected entries of b') as doubles
+// process group: keep the gathered rows whose user this rank trains (ownership rule of build_plan), zero the rest
+__global__ void zero_unowned_rows_kernel(double* dst, const int64_t* rows, int64_t n, int K, int64_t B, int64_t U,
+                                         int rank, int world) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * K) return;
+  const int64_t uid = rows[i / K];
+  const int64_t lo = (uid / B) * B;
+  const int64_t nb = min(B, U - lo);
+  const int64_t a = lo + (nb * rank) / world, b = lo + (nb * (rank + 1)) / world;
+  if (uid < a || uid >= b) dst[i] = 0.;
+}
+
 __global__ void gather_rows_to_double_kernel(double* dst, const float* src, const int64_t* rows,
                                              int64_t n, int K, int ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -762,7 +850,9 @@ int cdae_get_param_rows(cdae_handle* h, int which, const int64_t* rows, int64_t 
   if (which < 0 || which >= CDAE_P_COUNT || !p || r * c == 0) return set_error(CDAE_E_INVALID, "parameter block %d is absent", which);
   const bool vec = which == CDAE_P_B || which == CDAE_P_B_AG || which == CDAE_P_BPRIME || which == CDAE_P_BPRIME_AG;
   const bool user_block = which == CDAE_P_WU || which == CDAE_P_WU_AG || which == CDAE_P_UU || which == CDAE_P_UU_AG;
-  if (h->world > 1 && user_block) return set_error(CDAE_E_STATE, "row reads of user-private blocks are single-process; use cdae_get_param");
+  const bool item_acc_block = which == CDAE_P_W_AG || which == CDAE_P_V_AG || which == CDAE_P_B_AG || which == CDAE_P_BPRIME_AG;
+  if (h->world > 1 && item_acc_block && h->p2p_on && h->p2p_fused)
+    return set_error(CDAE_E_STATE, "accumulators are sharded across ranks in peer-memory mode; use cdae_get_param");
   const int64_t limit = vec ? c : r;   // vectors: `rows` index the entries
   for (int64_t i = 0; i < n; ++i)
     if (rows[i] < 0 || rows[i] >= limit) return set_error(CDAE_E_INVALID, "row %lld outside [0,%lld)", (long long)rows[i], (long long)limit);
@@ -773,6 +863,12 @@ int cdae_get_param_rows(cdae_handle* h, int which, const int64_t* rows, int64_t 
   CU(cudaMemcpyAsync(rows_d, rows, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
   gather_rows_to_double_kernel<<<cdiv(n * K, 256), 256, 0, h->stream>>>(h->stage_d.p, p, rows_d, n, K, L);
   KERNEL_OK(h);
+  if (h->world > 1 && user_block) {
+    // user rows are only current on the rank that trains them: zero the others, sum across ranks (collective)
+    zero_unowned_rows_kernel<<<cdiv(n * K, 256), 256, 0, h->stream>>>(h->stage_d.p, rows_d, n, K, h->batch_users, h->U, h->rank, h->world);
+    KERNEL_OK(h);
+    NC(g_nccl.AllReduce(h->stage_d.p, h->stage_d.p, (size_t)(n * K), kNcclDouble, kNcclSum, (ncclComm_t)h->comm, h->stream));
+  }
   CU(cudaMemcpyAsync(dst, h->stage_d.p, sizeof(double) * n * K, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -894,9 +990,27 @@ static int stage_users(cdae_handle* h, const int64_t* uids, int64_t n, bool want
 int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8_t* keep_mask,
                      const int32_t* negatives, cdae_epoch_stats_t* stats) {
   if (!h || !uids || n <= 0) return set_error(CDAE_E_INVALID, "need a non-empty uid list");
-  if (h->world > 1) return set_error(CDAE_E_STATE, "cdae_train_users is single-process (explicit inputs)");
   TRY(begin_call(h));
   h->topn_k = 0;  // stored recommendation lists are stale
+  if (h->world > 1) {
+    // process group (collective; every rank passes the SAME arguments): rank r trains slice r of the list —
+    // the rule of build_plan — and the minibatch is combined like any other.  stats are this rank's part.
+    {
+      std::vector<int64_t> sorted(uids, uids + n);
+      std::sort(sorted.begin(), sorted.end());
+      if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) return set_error(CDAE_E_INVALID, "uids must be distinct inside one frozen minibatch");
+    }
+    const int64_t a = n * h->rank / h->world, b = n * (h->rank + 1) / h->world;
+    int64_t off = 0;
+    for (int64_t i = 0; i < a; ++i) {
+      if (uids[i] < 0 || uids[i] >= h->U) return set_error(CDAE_E_INVALID, "uid %lld outside [0,%lld)", (long long)uids[i], (long long)h->U);
+      off += h->row_ptr_h[uids[i] + 1] - h->row_ptr_h[uids[i]];
+    }
+    uids += a;
+    n = b - a;
+    if (keep_mask) keep_mask += off;
+    if (negatives) negatives += off * h->cfg.num_neg;
+  }
   int64_t slots = 0, n_in = 0, n_out = 0;
   TRY(stage_users(h, uids, n, true, &slots, &n_in, &n_out));
   if (slots > 0 && !keep_mask) return set_error(CDAE_E_INVALID, "keep_mask is NULL");
@@ -990,15 +1104,25 @@ int cdae_data_loss(cdae_handle* h, uint64_t seed, double* out) {
 int cdae_penalty_loss(cdae_handle* h, double* out) {
   if (!h || !out) return set_error(CDAE_E_INVALID, "NULL argument");
   CU(cudaSetDevice(h->cfg.device));
-  TRY(ensure(h, h->stage_d, 1));
-  CU(cudaMemsetAsync(h->stage_d.p, 0, sizeof(double), h->stream));
   struct { const float* p; int64_t n; } blocks[5] = {
       {h->m.W, h->I * h->ld}, {h->m.V, h->m.V ? h->I * h->ld : 0}, {h->m.Wu, h->m.Wu ? h->U * h->ld : 0},
       {h->m.b, h->ld}, {h->m.bp, h->I4}};
-  if (h->world > 1 && h->m.Wu) return set_error(CDAE_E_STATE, "penalty_loss with user_factor in a process group: fetch Wu with cdae_get_param instead");
+  TRY(ensure(h, h->stage_d, 2));
+  CU(cudaMemsetAsync(h->stage_d.p, 0, 2 * sizeof(double), h->stream));
   for (auto& b : blocks) {
     if (!b.p || b.n == 0) continue;  // pad entries are exactly 0 and do not contribute
+    if (h->world > 1 && b.p == h->m.Wu) continue;
     sumsq_kernel<<<std::min(cdiv(b.n, 256), h->sm_count * 8), 256, 0, h->stream>>>(b.p, b.n, h->stage_d.p);
+    KERNEL_OK(h);
+  }
+  if (h->world > 1 && h->m.Wu) {
+    // Wu rows are current only on their owning rank: each rank sums the squares of the rows it trains into
+    // a second slot, the slots are summed across ranks (collective), the replicated item side counts once
+    sumsq_owned_rows_kernel<<<std::min(cdiv(h->U * h->ld, 256), h->sm_count * 8), 256, 0, h->stream>>>(
+        h->m.Wu, h->U, h->ld, h->batch_users, h->rank, h->world, h->stage_d.p + 1);
+    KERNEL_OK(h);
+    NC(g_nccl.AllReduce(h->stage_d.p + 1, h->stage_d.p + 1, 1, kNcclDouble, kNcclSum, (ncclComm_t)h->comm, h->stream));
+    add_double_kernel<<<1, 1, 0, h->stream>>>(h->stage_d.p, h->stage_d.p + 1);
     KERNEL_OK(h);
   }
   double s = 0.;
@@ -1032,20 +1156,45 @@ int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl
   return 0;
 }
 
-int cdae_dist_p2p_export(cdae_handle* h, void* out128) {
-  if (!h || !out128) return set_error(CDAE_E_INVALID, "NULL argument");
+// Peer-memory mode, step 1: switch the gradients to two ping-pong buffers (the fused step zeroes the idle
+// one), allocate the flag array and export CUDA IPC handles of {gradient buffers, item-side parameter
+// buffer, flags} — 3 x 64 bytes in a 256-byte record.
+static int p2p_prepare(cdae_handle* h) {
+  if (h->p2p_my_flags) return 0;
+  CU(cudaStreamSynchronize(h->stream));
+  static const bool unfused = getenv("CDAE_B200_P2P_FUSED") && atoi(getenv("CDAE_B200_P2P_FUSED")) == 0;
+  h->p2p_fused = !unfused;
+  if (h->p2p_fused) {
+    float* two = nullptr;
+    CU(cudaMalloc(&two, 2 * sizeof(float) * h->grad_floats));
+    CU(cudaMemset(two, 0, 2 * sizeof(float) * h->grad_floats));
+    h->grad.release();
+    h->grad.p = two;
+    h->grad.cap = 2 * h->grad_floats;
+    h->p2p_parity = 0;
+    h->m.steps_slot = 0;
+    point_item_side(h, h->grad.p);
+  }
+  CU(cudaMalloc(&h->p2p_my_flags, 64 * sizeof(uint32_t)));
+  CU(cudaMemset(h->p2p_my_flags, 0, 64 * sizeof(uint32_t)));
+  h->p2p_done = reinterpret_cast<unsigned int*>(h->p2p_my_flags + 32);   // block counter, not touched by peers
+  return 0;
+}
+
+int cdae_dist_p2p_export(cdae_handle* h, void* out256) {
+  if (!h || !out256) return set_error(CDAE_E_INVALID, "NULL argument");
   if (h->world < 2 || h->world > p2p::MAX_RANKS) return set_error(CDAE_E_STATE, "needs a process group of 2..%d ranks (cdae_dist_init first)", p2p::MAX_RANKS);
   CU(cudaSetDevice(h->cfg.device));
-  if (!h->p2p_my_flags) {
-    CU(cudaMalloc(&h->p2p_my_flags, 64 * sizeof(uint32_t)));
-    CU(cudaMemset(h->p2p_my_flags, 0, 64 * sizeof(uint32_t)));
-  }
-  cudaIpcMemHandle_t hg, hf;
+  TRY(p2p_prepare(h));
+  cudaIpcMemHandle_t hg, hp, hf;
   CU(cudaIpcGetMemHandle(&hg, h->grad.p));
+  CU(cudaIpcGetMemHandle(&hp, h->item_params.p));
   CU(cudaIpcGetMemHandle(&hf, h->p2p_my_flags));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  memcpy(out128, &hg, 64);
-  memcpy((char*)out128 + 64, &hf, 64);
+  memset(out256, 0, 256);
+  memcpy(out256, &hg, 64);
+  memcpy((char*)out256 + 64, &hp, 64);
+  memcpy((char*)out256 + 128, &hf, 64);
   return 0;
 }
 
@@ -1056,17 +1205,22 @@ int cdae_dist_p2p_open(cdae_handle* h, const void* handles) {
   for (int r = 0; r < h->world; ++r) {
     if (r == h->rank) {
       h->p2p_bufs[r] = h->grad.p;
+      h->p2p_params[r] = h->item_params.p;
       h->p2p_flags[r] = h->p2p_my_flags;
       continue;
     }
-    cudaIpcMemHandle_t hg, hf;
-    memcpy(&hg, (const char*)handles + (size_t)r * 128, 64);
-    memcpy(&hf, (const char*)handles + (size_t)r * 128 + 64, 64);
-    void *pg = nullptr, *pf = nullptr;
+    cudaIpcMemHandle_t hg, hp, hf;
+    memcpy(&hg, (const char*)handles + (size_t)r * 256, 64);
+    memcpy(&hp, (const char*)handles + (size_t)r * 256 + 64, 64);
+    memcpy(&hf, (const char*)handles + (size_t)r * 256 + 128, 64);
+    void *pg = nullptr, *pp = nullptr, *pf = nullptr;
     CU(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
     CU(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
     h->p2p_bufs[r] = (float*)pg;
+    h->p2p_params[r] = (float*)pp;
     h->p2p_flags[r] = (uint32_t*)pf;
+    h->p2p_ipc = true;
   }
   h->p2p_epoch = 0;
   h->p2p_on = true;
@@ -1091,7 +1245,7 @@ int cdae_profile_get(cdae_handle* h, double* ms_out, int64_t* launches_out) {
 // 16-byte vector reduction into a second table (mode & 2), in the handle's own <G,NV> row geometry.
 int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits, int32_t reps,
                   double* gbs_out, double* ms_out) {
-  if (!h || !gbs_out || rows <= 0 || row_visits <= 0 || reps <= 0 || mode < 1 || mode > 3)
+  if (!h || !gbs_out || rows <= 0 || row_visits <= 0 || reps <= 0 || mode < 1 || mode > 5)
     return set_error(CDAE_E_INVALID, "bad argument");
   CU(cudaSetDevice(h->cfg.device));
   const int ld = h->ld;
@@ -1103,6 +1257,7 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
   CU(cudaMemsetAsync(src, 0, bytes, h->stream));
   CU(cudaMemsetAsync(dst, 0, bytes, h->stream));
   const int rows_per_warp = 192;                    // one output chunk of the decode: <= 96 rows, two chunks' worth
+  const uint32_t live_bytes = (uint32_t)((h->K * 4 + 15) / 16 * 16);   // modes 4, 5: bulk reductions of the real columns only
   const int n_warps = (int)((row_visits + rows_per_warp - 1) / rows_per_warp);
   const int grid = cdiv((int64_t)n_warps * 32, 256);
   cudaEvent_t e0, e1;
@@ -1115,7 +1270,9 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
     do {                                                                                                           \
       if (mode == 1) l2_probe_kernel<G, NV, 1><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
       else if (mode == 2) l2_probe_kernel<G, NV, 2><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
-      else l2_probe_kernel<G, NV, 3><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
+      else if (mode == 3) l2_probe_kernel<G, NV, 3><<<grid, 256, 0, h->stream>>>(src, dst, rows, ld, rows_per_warp, n_warps, (uint32_t)it * 7919u, sink); \
+      else if (mode == 4) l2_probe_bulk_kernel<G, NV, false><<<grid, 256, 0, h->stream>>>(src, dst, rows, rows_per_warp, n_warps, (uint32_t)it * 7919u, live_bytes, sink); \
+      else l2_probe_bulk_kernel<G, NV, true><<<grid, 256, 0, h->stream>>>(src, dst, rows, rows_per_warp, n_warps, (uint32_t)it * 7919u, live_bytes, sink); \
     } while (0)
     DISPATCH_LD(ld, CALL);
 #undef CALL
@@ -1131,7 +1288,10 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
   cudaFree(src); cudaFree(dst); cudaFree(sink);
   if (rc) return rc;
   const double per = ms / reps;
-  const double moved = (double)n_warps * rows_per_warp * ld * 4.0 * ((mode & 1) + ((mode >> 1) & 1));
+  // modes 4 / 5 (bulk reductions, without / with the row loads) are reported in the same units as 2 / 3:
+  // padded row bytes per visit, so the numbers compare as "rows per second"
+  const int eq = mode == 4 ? 2 : mode == 5 ? 3 : mode;
+  const double moved = (double)n_warps * rows_per_warp * ld * 4.0 * ((eq & 1) + ((eq >> 1) & 1));
   *gbs_out = moved / (per * 1e-3) / 1e9;
   if (ms_out) *ms_out = per;
   return 0;

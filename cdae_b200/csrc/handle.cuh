@@ -44,9 +44,14 @@ struct cdae_handle {
   void* comm = nullptr;  // ncclComm_t
   // NVLink peer-memory all-reduce (p2p_allreduce.cuh), opt-in through cdae_dist_p2p_open
   bool p2p_on = false;
-  float* p2p_bufs[8] = {nullptr};
+  bool p2p_fused = false;          // reduce-scatter + sliced optimiser step + all-gather in one kernel (default)
+  bool p2p_ipc = false;            // peer pointers came from cudaIpcOpenMemHandle (other processes)
+  float* p2p_bufs[8] = {nullptr};  // every rank's gradient buffer(s): base of [2][grad_floats] when fused
+  float* p2p_params[8] = {nullptr};  // every rank's item-side parameter buffer
   uint32_t* p2p_flags[8] = {nullptr};
   uint32_t* p2p_my_flags = nullptr;
+  unsigned int* p2p_done = nullptr;
+  int p2p_parity = 0;              // which gradient buffer the current minibatch accumulates into
   uint32_t p2p_epoch = 0;
   int sm_count = 148;
   size_t dev_bytes = 0;
@@ -54,7 +59,10 @@ struct cdae_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cdae::ModelDev m;
-  cdae::DevBuf<float> grad;
+  // item side: parameters, AdaGrad state and minibatch gradients as flat buffers of ONE layout
+  // (point_item_side in api.cu); h->m.W / V / bp / b and their *_ag / g* pointers point into them
+  cdae::DevBuf<float> item_params, item_acc;
+  cdae::DevBuf<float> grad;      // [grad_floats], or 2 x grad_floats (ping-pong) in peer-memory mode
   size_t grad_floats = 0;
 
   std::vector<int64_t> row_ptr_h;  // host copy (work lists depend on it)

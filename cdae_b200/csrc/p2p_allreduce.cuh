@@ -1,14 +1,31 @@
-// cdae_b200/csrc/p2p_allreduce.cuh — the per-minibatch gradient all-reduce over NVLink peer memory
-// (SURVEY.md §8e), written for this path instead of calling NCCL: every rank's gradient buffer and a
-// small flag array are mapped into every other rank (CUDA IPC), and one kernel per rank
-//   1. tells every peer "my gradients are complete" and waits until all peers said so,
-//   2. sums ITS 1/G slice of the buffer over all ranks with 16-byte loads straight from peer memory,
-//   3. writes the sum back into that slice of EVERY rank's buffer (two-shot all-reduce: reduce-scatter
-//      by peer loads, all-gather by peer stores; each byte crosses NVLink once in each direction),
-// followed by a one-block barrier kernel ("my stores are out" / "everybody's stores are in") before
-// apply_kernel reads the buffer.  At config B the buffer is 13.6 MB; NCCL's ring all-reduce of that
-// size is latency-bound at ~0.1 ms on 8 GPUs (32 % of an epoch's device time, profiles/r01_n_*).
-// Opt-in (cdae_dist_p2p_export / cdae_dist_p2p_open); NCCL stays the default and the fallback.
+// cdae_b200/csrc/p2p_allreduce.cuh — the per-minibatch combine step of the data-parallel path
+//  as ONE kernel over NVLink peer memory instead of "NCCL all-reduce, then the same
+// dense optimiser pass on every rank":
+//
+//     reduce-scatter (peer loads)  ->  optimiser step on the rank's 1/G slice  ->  all-gather (peer stores)
+//
+// Every rank's gradient buffer, item-side parameter buffer and a small flag array are mapped into
+// every other rank (CUDA IPC).  The three item-side buffers share one layout (point_item_side in
+// api.cu), so the whole step is a flat elementwise pass.  One launch per rank and minibatch:
+//   1. block 0 tells every peer "my gradients are complete" (system-scope release store into the
+//      peer's flags); every block waits until all peers said so;
+//   2. the rank sums ITS 1/G slice of the gradient buffer over all ranks with 16-byte loads straight
+//      from peer memory, in rank order (the sum is a pure function of the G buffers);
+//   3. it applies upd() (AdaGrad or SGD, cdae.hpp:253-257) to that slice with ITS accumulator slice —
+//      accumulators are sharded: only the owner of a slice keeps them current — and
+//   4. stores the updated parameters into that slice of EVERY rank's parameter buffer (elements whose
+//      gradient is exactly zero are skipped: nothing changed, nothing crosses the wire);
+//   5. meanwhile it zeroes the OTHER gradient buffer (gradients ping-pong between two buffers, so the
+//      one the previous minibatch consumed is cleared here, off the critical path);
+//   6. the last block to finish announces "my stores are out" and waits for the same from every peer —
+//      when the kernel ends, this rank's parameters are complete and its gradients have been read.
+// Each gradient byte crosses NVLink once (as a load), each parameter byte once (as a store): the
+// traffic of a two-shot all-reduce, with 1/G of the optimiser work per rank and no second pass
+// over the buffer.  At config B the buffer is 13.6 MB (NCCL's all-reduce of it: ~100 us on 8 GPUs,
+// latency-bound); at config D it is 102 MB and the dense apply it replaces streams 614 MB per rank.
+//
+// `reduce_kernel` / `barrier_kernel` (plain two-shot all-reduce followed by the replicated
+// apply_kernel) are kept as the A/B baseline (CDAE_B200_P2P_FUSED=0).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,18 +56,23 @@ __device__ __forceinline__ float4 ld_sys_v4(const float* p) {
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ float ld_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_sys_v4(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // announce `epoch` to every rank (one thread per peer) — call from ONE block, after a system fence
-__device__ __forceinline__ void announce(const Args& a) {
-  if ((int)threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
+__device__ __forceinline__ void announce(uint32_t* const* flags, int rank, int world, uint32_t epoch) {
+  if ((int)threadIdx.x < world) st_release_sys(flags[threadIdx.x] + rank, epoch);
 }
 // every calling block waits until all ranks announced `epoch` to this rank
-__device__ __forceinline__ void wait_all(const Args& a) {
-  if ((int)threadIdx.x < a.world)
-    while ((int32_t)(ld_acquire_sys(a.flags[a.rank] + threadIdx.x) - a.epoch) < 0) {}
+__device__ __forceinline__ void wait_all(uint32_t* const* flags, int rank, int world, uint32_t epoch) {
+  if ((int)threadIdx.x < world)
+    while ((int32_t)(ld_acquire_sys(flags[rank] + threadIdx.x) - epoch) < 0) {}
   __syncthreads();
 }
 
@@ -58,9 +80,9 @@ __global__ void __launch_bounds__(512) reduce_kernel(Args a) {
   // stream order: every kernel that added to this rank's gradients has finished
   if (blockIdx.x == 0) {
     __threadfence_system();
-    announce(a);
+    announce(a.flags, a.rank, a.world, a.epoch);
   }
-  wait_all(a);
+  wait_all(a.flags, a.rank, a.world, a.epoch);
   const int64_t lo = a.n4 * a.rank / a.world, hi = a.n4 * (a.rank + 1) / a.world;
   for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -79,8 +101,121 @@ __global__ void __launch_bounds__(512) reduce_kernel(Args a) {
 // "my stores are out" -> "everybody's stores are in"; a.epoch is the SECOND value of the minibatch
 __global__ void __launch_bounds__(32) barrier_kernel(Args a) {
   __threadfence_system();
-  announce(a);
-  wait_all(a);
+  announce(a.flags, a.rank, a.world, a.epoch);
+  wait_all(a.flags, a.rank, a.world, a.epoch);
+}
+
+// ---------------------------------------------------------------------------------------
+// The fused combine step (see the file comment).
+struct FusedArgs {
+  float* grads[MAX_RANKS];         // every rank's CURRENT gradient buffer
+  float* params[MAX_RANKS];        // every rank's item-side parameter buffer
+  uint32_t* flags[MAX_RANKS];
+  float* acc;                      // this rank's accumulator buffer (only [lo, hi) is kept current)
+  float* grad_next;                // this rank's OTHER gradient buffer: zeroed here for the next minibatch
+  unsigned int* done;              // this rank's block counter (self-resetting)
+  int* bad_csr_out;                // StatsDev::bad_csr
+  int rank, world;
+  uint32_t epoch;                  // announces epoch (gradients complete) and epoch + 1 (stores out)
+  int64_t n4;                      // float4 count of one buffer
+  // layout, in float4 units: [0, w_end) = W and V rows of ld4 float4; [w_end, bp_end) = b';
+  // [bp_end, b_lo) = kept-input counts (two slots of cnt4 float4, no parameters); [b_lo, b_hi) = b; then steps
+  int64_t w_rows_end;              // I*ld4 (only W rows carry the lambda*count*W term)
+  int64_t w_end, bp_end, b_lo, b_hi;
+  int ld4;
+  int64_t cnt_off;                 // float offset of the active counts slot
+  int64_t steps_off;               // float offset of steps[0..3] ([slot] user steps, [2] bad-CSR flag)
+  int steps_slot;
+  float lr, beta, lambda;
+  int adagrad;
+};
+
+__global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    announce(a.flags, a.rank, a.world, a.epoch);
+  }
+  // zero the gradient buffer the previous minibatch consumed while the announcements travel
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (int64_t)gridDim.x * blockDim.x)
+    *reinterpret_cast<float4*>(a.grad_next + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  wait_all(a.flags, a.rank, a.world, a.epoch);
+
+  // scalars every element may need: user steps of the minibatch (n * lambda * b) and the bad-CSR flag
+  float steps = 0.f, bad = 0.f;
+#pragma unroll
+  for (int p = 0; p < MAX_RANKS; ++p)
+    if (p < a.world) {
+      steps += ld_sys_f32(a.grads[p] + a.steps_off + a.steps_slot);
+      bad += ld_sys_f32(a.grads[p] + a.steps_off + 2);
+    }
+  const bool discard = bad != 0.f;
+  if (discard && blockIdx.x == 0 && threadIdx.x == 0) *a.bad_csr_out = 1;
+
+  const int64_t lo = a.n4 * a.rank / a.world, hi = a.n4 * (a.rank + 1) / a.world;
+  float* const my_params = a.params[a.rank];
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= a.bp_end && i < a.b_lo) continue;      // counts: no parameter behind them
+    if (i >= a.b_hi) continue;                      // steps / flag
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < MAX_RANKS; ++p)
+      if (p < a.world) {
+        const float4 v = ld_sys_v4(a.grads[p] + i * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    float lin = 0.f;                                // coefficient of w in the gradient: lambda * (count | steps)
+    if (i < a.w_rows_end) {
+      if (a.lambda != 0.f) {
+        float c = 0.f;
+        const int64_t row = i / a.ld4;
+#pragma unroll
+        for (int p = 0; p < MAX_RANKS; ++p)
+          if (p < a.world) c += ld_sys_f32(a.grads[p] + a.cnt_off + row);
+        lin = a.lambda * c;
+      }
+    } else if (i >= a.b_lo) {
+      lin = a.lambda * steps;
+    }
+    if (discard) continue;
+    if (lin == 0.f && s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;   // untouched: identical everywhere already
+    const float4 w4 = *reinterpret_cast<const float4*>(my_params + i * 4);
+    float g[4] = {s.x, s.y, s.z, s.w};
+    float w[4] = {w4.x, w4.y, w4.z, w4.w};
+    if (lin != 0.f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] += lin * w[k];
+    }
+    if (a.adagrad) {
+      const float4 a4 = *reinterpret_cast<const float4*>(a.acc + i * 4);
+      float ac[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (g[k] == 0.f) continue;                  // upd(0) is a no-op (and no 0/0 in pad columns when beta = 0)
+        ac[k] += g[k] * g[k];
+        g[k] = g[k] / (a.beta + sqrtf(ac[k]));
+      }
+      *reinterpret_cast<float4*>(a.acc + i * 4) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
+    const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int p = 0; p < MAX_RANKS; ++p)
+      if (p < a.world) st_sys_v4(a.params[p] + i * 4, wn);
+  }
+
+  // last block out: "my stores are out" -> wait until everybody's are in
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *a.done = 0u;
+    __threadfence_system();
+    announce(a.flags, a.rank, a.world, a.epoch + 1);
+    wait_all(a.flags, a.rank, a.world, a.epoch + 1);
+  }
 }
 
 }  // namespace p2p

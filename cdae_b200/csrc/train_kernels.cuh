@@ -302,74 +302,140 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
 // Tied weights and o in the corrupted input: the lambda term is left to scatter_kernel so the
 // row receives ONE lambda per merged occurrence (cdae.hpp:249-250, 342-343).
 // TRAIN=false scores the positives only and accumulates loss(y,1): CDAE::data_loss :93-96.
+// Resident CTAs per SM the register allocation must allow, and row batches in flight per warp.  The kernel
+// is latency-bound (dependent chain LDS -> LDG -> dot -> shuffles -> SFU -> RED), so occupancy beats
+// per-warp unrolling: measured at config B (profiles/r02_b_*) UNR 4 / 3 CTAs 104.6 us per 8,192 users,
+// UNR 2 / 4 CTAs 100.4, UNR 1 / 5 CTAs 99.4, UNR 2 / 5 CTAs (spills) 118.7, UNR 4 / 2 CTAs 119.1.
 #ifndef DECODE_MIN_BLOCKS
-#define DECODE_MIN_BLOCKS 3  // resident CTAs per SM the register allocation must allow (A/B: tools/ab_build.sh)
+#define DECODE_MIN_BLOCKS 0  // 0 = by geometry: 4 for NV <= 2, else 3
+#endif
+#ifndef DECODE_UNR
+#define DECODE_UNR 0       // row batches in flight per warp; 0 = by geometry: 4 for NV = 1, 2 for NV = 2, 3, 1 for NV = 4 (no spills at the register cap)
 #endif
 constexpr int DECODE_MAX_NEGS = 96;  // ch_out * num_neg <= 96 by construction (api.cu)
+constexpr int DECODE_MAX_ROWS = 96;  // outputs of one chunk: n * (1 + num_neg) <= 96
+
+// SFU forms of the CROSS_ENTROPY loss (loss.hpp:132-147): one ex2, one rcp, one lg2 — the library
+// __expf / __frcp_rn wrap these in range fix-ups (denormal scaling, a Newton step behind a slow-path
+// branch) that cost ~12 issue slots per output for nothing at |y| <= 18 (profiles/r02_a_*).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// dl/dy and l(y, t) for CROSS_ENTROPY, branch-free (same functions as loss_grad's LOSS_CE case)
+__device__ __forceinline__ float ce_grad(float y, float t, float* loss) {
+  const float a = ex2_approx(-1.4426950408889634f * fabsf(y));   // e^-|y|
+  const float d = 1.f + a;
+  const float r = rcp_approx(d);
+  *loss = fmaf(lg2_approx(d), 0.6931471805599453f, fmaf(1.f - t, y, fmaxf(-y, 0.f)));
+  return (y >= 0.f ? r : a * r) - t;
+}
+// 16-byte reduction issued only where `on` != 0: a predicated instruction, not a branch
+__device__ __forceinline__ void red_add_v4_if(float* addr, float4 v, int on) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void red_add_f32_if(float* addr, float v, int on) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(on)
+               : "memory");
+}
+
 // LT >= 0 fixes the loss at compile time (CROSS_ENTROPY and SQUARE, the two that are meaningful for
-// CDAE): the 7-way switch of loss_grad() and its copies in the unrolled row loop
-// were ~25% of the executed instructions (BRA/BSSY/BSYNC/ISETP, profiles/r01_b_*).  LT = -1 reads
-// m.loss at run time.
+// CDAE); LT = -1 reads m.loss at run time.
+//
+// Structure (round 2; profiles/r02_a_*: the round-1 kernel spent 122 issue slots per 4-row batch, ~70 of
+// them on index plumbing — four BSSY/BRA blocks choosing between the positive list in global memory and
+// the negative list in shared memory, 64-bit row-address arithmetic with the run-time leading dimension,
+// library exp / rcp fix-ups — and spilled under its 80-register cap):
+//   * the chunk's output list (positives, then negatives) is staged ONCE in shared memory, one word per
+//     output: item id | merged flag in bit 31; the row loop reads it with one LDS per batch, no branches;
+//   * the leading dimension is the compile-time constant 4*G*NV, so a row address is one IMAD.WIDE;
+//   * 16-byte pieces that lie entirely in the padding (columns >= K: 3 of 16 at K = 50) are neither
+//     loaded nor reduced — a per-lane predicate hoisted out of the loop, applied with predicated
+//     instructions (the L2's vector-reduction throughput is this kernel's roofline, bench.py `peak_l2`);
+//   * rows past the end of the chunk ride along with g = 0 and their reductions predicated off.
 template <int G, int NV, bool TRAIN, bool SAMPLED, int LT>
-__global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS) decode_kernel(ModelDev m, BatchDev bt, SampleArgs sa,
-                                                     StatsDev* stats) {
+__global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS > 0 ? DECODE_MIN_BLOCKS : (NV <= 2 ? 4 : 3))
+    decode_kernel(ModelDev m, BatchDev bt, SampleArgs sa, StatsDev* stats) {
   using RM = RowMap<G, NV>;
-  constexpr int NG = RM::NG, UNR = RM::UNR;
-  __shared__ int32_t negs_s[SAMPLED && TRAIN ? 8 : 1][SAMPLED && TRAIN ? DECODE_MAX_NEGS : 1];
+  constexpr int NG = RM::NG, UNR = DECODE_UNR > 0 ? DECODE_UNR : (NV == 1 ? 4 : NV <= 3 ? 2 : 1), LD = 4 * G * NV;
+  constexpr int LIST = DECODE_MAX_ROWS + 1 + NG * UNR;   // (num_neg = 96: 97 rows) + one batch of slack
+  __shared__ int32_t rows_s[8][LIST];    // the chunk's outputs: positives, then negatives
+  __shared__ float lam_s[8][LIST];       // lambda of each output's row term (0 for a merged positive)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= bt.n_out_items) return;
   const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
   const WorkItem wi = load_item(bt.out_items + warp);
-  const int32_t* pos = bt.col + wi.s0;
-  const uint8_t* keep = bt.keep + wi.aux0;
-  const int32_t* neg = bt.negs + (int64_t)wi.aux0 * m.nu;
-  if (SAMPLED && TRAIN) {
-    int32_t* mine = negs_s[threadIdx.x >> 5];
-    sample_negs_chunk(wi, sa, m.nu, m.I, bt.row_ptr, bt.col, mine, lane);
-    __syncwarp();
-    neg = mine;
-  }
-  const float* Wd = m.asym ? m.V : m.W;
-  float* gWd = m.asym ? m.gV : m.gW;
   const int n = wi.n;
   const int R = TRAIN ? n * (1 + m.nu) : n;
-  const bool tied = !m.asym;
+  int32_t* mine = rows_s[threadIdx.x >> 5];
+  float* lam_mine = lam_s[threadIdx.x >> 5];
+  const float lambda = m.lambda;
+  {
+    // merged occurrence (tied weights, the positive is also a kept input): its lambda term is left to
+    // scatter_kernel so the row receives ONE lambda per merged occurrence (cdae.hpp:249-250, 342-343)
+    const bool tied = !m.asym;
+    const int32_t* pos = bt.col + wi.s0;
+    const uint8_t* keep = bt.keep + wi.aux0;
+    for (int r = lane; r < R + NG * UNR; r += 32) lam_mine[r] = r < R ? lambda : 0.f;
+    __syncwarp();
+    for (int r = lane; r < n; r += 32) {
+      mine[r] = __ldg(pos + r);
+      if (TRAIN && tied && keep[r]) lam_mine[r] = 0.f;
+    }
+    // slack behind the list: a valid row, so the last (partial) batch loads without bound checks
+    if (lane < NG * UNR) mine[R + lane] = __ldg(pos);
+    if (TRAIN) {
+      if (SAMPLED) {
+        sample_negs_chunk(wi, sa, m.nu, m.I, bt.row_ptr, bt.col, mine + n, lane);
+      } else {
+        const int32_t* neg = bt.negs + (int64_t)wi.aux0 * m.nu;
+        for (int j = lane; j < R - n; j += 32) mine[n + j] = neg[j];
+      }
+    }
+    __syncwarp();
+  }
+  // compile-time leading dimension: a row address is base + id * (4*LD) = one IMAD.WIDE
+  const float* Wl = (m.asym ? m.V : m.W) + gl * 4;
+  float* gWl = (m.asym ? m.gV : m.gW) + gl * 4;
 
   float4 z[NV], hg[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const int c = RM::col4(gl, v);
-    z[v] = ld4(bt.Z + (int64_t)wi.u_local * m.ld + c);
+    z[v] = ld4(bt.Z + (int64_t)wi.u_local * LD + RM::col4(gl, v));
     hg[v] = f4zero();
   }
+  // Only the LAST piece of a lane can lie entirely in the padding: DISPATCH_LD picks the smallest NV
+  // with 4*G*NV >= K, so K > 4*G*(NV-1) and the pieces v < NV-1 hold real columns in every lane.
+  const int last_live = RM::col4(gl, NV - 1) < m.K;
   float loss_acc = 0.f;
   int bad = 0;
+  const int first = gl == 0;
 
   for (int base = 0; base < R; base += NG * UNR) {
-    int it[UNR];
-    bool merged[UNR];
+    int id[UNR];
 #pragma unroll
-    for (int t = 0; t < UNR; ++t) {
-      const int r = base + t * NG + grp;
-      it[t] = -1;
-      merged[t] = false;
-      if (r < n) {
-        it[t] = __ldg(pos + r);
-        merged[t] = TRAIN && tied && keep[r];
-      } else if (r < R) {
-        it[t] = neg[r - n];
-      }
-    }
+    for (int t = 0; t < UNR; ++t) id[t] = mine[base + t * NG + grp];
     float4 w[UNR][NV];
     float bp[UNR];
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = RM::col4(gl, v);
-        w[t][v] = it[t] >= 0 ? ld4(Wd + (int64_t)it[t] * m.ld + c) : f4zero();
-      }
-      bp[t] = it[t] >= 0 ? __ldg(m.bp + it[t]) : 0.f;
+      for (int v = 0; v < NV; ++v) w[t][v] = ld4(Wl + (int64_t)id[t] * LD + v * G * 4);   // pad pieces read zeros
+      bp[t] = __ldg(m.bp + id[t]);
     }
     float y[UNR];
 #pragma unroll
@@ -380,26 +446,31 @@ __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS) decode_kernel(ModelDev
       y[t] = p;
     }
 #pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1)
+    for (int off_ = G / 2; off_ > 0; off_ >>= 1)
 #pragma unroll
-      for (int t = 0; t < UNR; ++t) y[t] += __shfl_xor_sync(0xffffffffu, y[t], off);
+      for (int t = 0; t < UNR; ++t) y[t] += __shfl_xor_sync(0xffffffffu, y[t], off_);
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
-      if (it[t] < 0) continue;  // uniform inside the group
+      if (base + t * NG >= R) break;          // warp-uniform: whole batches past the end of the chunk
       const int r = base + t * NG + grp;
+      const float ok = r < R ? 1.f : 0.f;     // a row past the end inside the last batch adds exact zeros
       const float truth = r < n ? 1.f : 0.f;
-      float l;
-      const float g = loss_grad(LT >= 0 ? LT : m.loss, y[t] + bp[t], truth, &l, &bad);
-      if (gl == 0) loss_acc += l;
+      float l, g;
+      if (LT == LOSS_CE) g = ce_grad(y[t] + bp[t], truth, &l);
+      else g = loss_grad(LT >= 0 ? LT : m.loss, y[t] + bp[t], truth, &l, &bad);
+      g *= ok;
+      loss_acc = fmaf(ok, l, loss_acc);
       if (!TRAIN) continue;
-      const float lam = merged[t] ? 0.f : m.lambda;
+      const float lam = lam_mine[r];          // 0 in the slack
+      float* grow = gWl + (int64_t)id[t] * LD;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const int c = RM::col4(gl, v);
         hg[v] = fma4(g, w[t][v], hg[v]);
-        red_add_v4(gWd + (int64_t)it[t] * m.ld + c, fma4(g, z[v], scale4(lam, w[t][v])));
+        const float4 gr = fma4(g, z[v], scale4(lam, w[t][v]));
+        if (v < NV - 1) red_add_v4(grow + v * G * 4, gr);
+        else red_add_v4_if(grow + v * G * 4, gr, last_live);
       }
-      if (gl == 0) red_add_f32(m.gbp + it[t], g + m.lambda * bp[t]);
+      red_add_f32_if(m.gbp + id[t], ok * fmaf(lambda, bp[t], g), first);
     }
   }
   if (TRAIN) {
@@ -407,10 +478,10 @@ __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS) decode_kernel(ModelDev
     for (int v = 0; v < NV; ++v) {
       hg[v] = cross_group_sum<G>(hg[v]);
       const int c = RM::col4(gl, v);
-      if (grp == 0) red_add_v4(bt.HG + (int64_t)wi.u_local * m.ld + c, hg[v]);
+      if (grp == 0) red_add_v4(bt.HG + (int64_t)wi.u_local * LD + c, hg[v]);
     }
   }
-  loss_acc = group_sum<32>(loss_acc);
+  loss_acc = group_sum<32>(first ? loss_acc : 0.f);
   bad = __any_sync(0xffffffffu, bad);
   if (lane == 0) {
     atomicAdd(&stats->loss_sum[warp % STAT_STRIPES], (double)loss_acc);
@@ -693,6 +764,41 @@ __global__ void owned_rows_kernel(float* dst, const float* src, int64_t rows, in
   const int64_t n = min(B, U - lo);
   const int64_t a = lo + (n * rank) / world, b = lo + (n * (rank + 1)) / world;
   dst[i] = (uid >= a && uid < b) ? src[i] : 0.f;
+}
+
+// the part of an item-side block that lies inside this rank's slice [lo, hi) of the flat buffer
+__global__ void owned_flat_kernel(float* dst, const float* src, int64_t n, int64_t block_off, int64_t lo, int64_t hi) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t f = block_off + i;
+  dst[i] = (f >= lo && f < hi) ? src[i] : 0.f;
+}
+__global__ void add_double_kernel(double* dst, const double* src) { *dst += *src; }
+
+// sum of squares of the user rows this rank trains (ownership rule of build_plan)
+__global__ void __launch_bounds__(256) sumsq_owned_rows_kernel(const float* src, int64_t U, int ld, int64_t B, int rank,
+                                                               int world, double* out) {
+  double s = 0.;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U * ld; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t uid = i / ld;
+    const int64_t lo = (uid / B) * B;
+    const int64_t nb = min(B, U - lo);
+    const int64_t a = lo + (nb * rank) / world, b = lo + (nb * (rank + 1)) / world;
+    if (uid >= a && uid < b) {
+      const double v = src[i];
+      s += v * v;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    atomicAdd(out, t);
+  }
 }
 
 // sum of squares, double accumulation (CDAE::penalty_loss, cdae.hpp:103-107 / penalty.hpp:36-39)

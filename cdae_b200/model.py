@@ -139,6 +139,14 @@ class CDAE:
             _lib.check(self._L.cdae_get_param(self._h, PARAM_ID[name], _ptr(a, _lib.f64p), a.size))
         return a.reshape(r, c) if c > 1 else a
 
+    def _get_rows(self, name, rows):
+        """Selected rows of a block (cdae_get_param_rows; collective for user blocks in a process group)."""
+        r = _arr(rows, np.int64)
+        _, c = self.param_shape(name)
+        out = np.zeros((len(r), max(c, 1)))
+        _lib.check(self._L.cdae_get_param_rows(self._h, PARAM_ID[name], _ptr(r, _lib.i64p), len(r), _ptr(out, _lib.f64p)))
+        return out
+
     def get_params(self):
         return {k: self.get_param(k) for k in PARAMS}
 
@@ -274,7 +282,7 @@ class CDAE:
     def dist_p2p_init(self, all_gather):
         """Switch the gradient all-reduce to the NVLink peer-memory kernel.  `all_gather(bytes) ->
         list of bytes in rank order` is the caller's collective (e.g. torch.distributed.all_gather_object)."""
-        buf = (C.c_char * 128)()
+        buf = (C.c_char * 256)()
         _lib.check(self._L.cdae_dist_p2p_export(self._h, buf))
         table = b"".join(all_gather(bytes(buf)))
         tb = C.create_string_buffer(table, len(table))

@@ -96,7 +96,8 @@ typedef struct cdae_epoch_stats {
   int64_t user_steps;         /* (user, corruption) pairs trained                     */
   int64_t outputs;            /* positives + negatives scored                          */
   int64_t inputs_kept;        /* input items that survived corruption                  */
-  double loss_sum;            /* sum over scored outputs of loss(y, t)                 */
+  double loss_sum;            /* sum over scored outputs of loss(y, t); 0 with full_decode (the tensor-core
+                                 epilogue only forms the loss GRADIENT; use cdae_data_loss) */
   double device_ms;           /* device time of the call, CUDA events on the handle's stream */
   int64_t kernel_launches;    /* kernels this call launched                            */
   int64_t h2d_bytes, d2h_bytes; /* bytes this call copied across PCIe                  */
@@ -228,13 +229,17 @@ int cdae_load(cdae_handle* h, const char* path);
 int cdae_dist_unique_id(void* id128_out);
 int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id);
 
-/* Optional: replace the per-minibatch NCCL all-reduce by a two-shot all-reduce over NVLink peer
- * memory written for this path (csrc/p2p_allreduce.cuh): every rank exports CUDA IPC handles of its
- * gradient buffer and flag array (128 bytes), the caller gathers them in rank order (world x 128
- * bytes) and hands the table to every rank.  Needs cdae_dist_init first, 2..8 ranks on one node with
- * peer access; every rank must open before the next training call.  NCCL remains in use for
- * everything else (parameter read-back, data_loss). */
-int cdae_dist_p2p_export(cdae_handle* h, void* handles128_out);
+/* Peer-memory mode of the per-minibatch combine step (csrc/p2p_allreduce.cuh): instead of an NCCL
+ * all-reduce followed by the same dense optimiser pass on every rank, ONE kernel per rank reduce-scatters
+ * the gradients with loads from NVLink peer memory, applies the optimiser step to the rank's 1/G slice
+ * (AdaGrad state is sharded: a rank keeps only its slice current) and all-gathers the updated
+ * parameters with peer stores.  Every rank exports CUDA IPC handles of its gradient buffers, its
+ * item-side parameter buffer and its flag array (a 256-byte record), the caller gathers the records in
+ * rank order (world x 256 bytes) and hands the table to every rank.  Needs cdae_dist_init first, 2..8
+ * ranks on one node with peer access; every rank must open before the next training call.  NCCL remains
+ * in use for everything else (parameter read-back, data_loss).  cdae_get_param of an accumulator block
+ * assembles the slices (collective). */
+int cdae_dist_p2p_export(cdae_handle* h, void* record256_out);
 int cdae_dist_p2p_open(cdae_handle* h, const void* all_handles);
 
 /* Per-kernel-class device timing for benchmarks: when enabled, every kernel launch is

@@ -22,6 +22,24 @@ WANT = [
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
     ("smsp__inst_executed.sum", "warp_inst"),
+    # L2 side of the gather / reduction kernels
+    ("lts__t_sectors.sum", "l2_sectors"),
+    ("lts__t_sectors_srcunit_tex_op_read.sum", "l2_sectors_read"),
+    ("lts__t_sectors_srcunit_tex_op_write.sum", "l2_sectors_write"),
+    ("lts__t_sectors_srcunit_tex_op_red.sum", "l2_sectors_red"),
+    ("lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed", "l2_red_pct"),
+    ("lts__t_sectors_srcunit_tex_op_atom.sum", "l2_sectors_atom"),
+    ("lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed", "l2_atomic_unit_pct"),
+    ("lts__t_sectors.sum.pct_of_peak_sustained_elapsed", "l2_sectors_pct"),
+    ("lts__lts2xbar_cycles_active.avg.pct_of_peak_sustained_elapsed", "l2_to_xbar_pct"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "xbar2l1_read"),
+    ("l1tex__m_l1tex2xbar_write_bytes.sum", "l12xbar_write"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "ld_requests"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "red_requests"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "ld_sectors"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "red_sectors"),
+    ("sm__cycles_elapsed.max", "cycles"),
 ]
 
 
@@ -41,6 +59,16 @@ def main(path):
         for h in tensor_cols:
             if r[idx[h]] not in ("", "n/a", "0"):
                 print("    %-16s %s %s" % (h[:60], r[idx[h]], units[idx[h]]))
+        # warp-stall breakdown: cycles a warp waits per issued instruction, by reason (top 6)
+        stalls = []
+        for h in hdr:
+            if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio") and r[idx[h]] not in ("", "n/a"):
+                try:
+                    stalls.append((float(r[idx[h]].replace(",", "")), h))
+                except ValueError:
+                    pass
+        for v, h in sorted(stalls, reverse=True)[:6]:
+            print("    stall %-28s %.2f warps per issued instruction" % (h.split("issue_stalled_")[-1].replace("_per_issue_active.ratio", ""), v))
 
 
 if __name__ == "__main__":
