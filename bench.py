@@ -524,9 +524,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx.sms = torch.cuda.get_device_properties(local).multi_processor_count
     ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    # the combine step: one fused kernel over NVLink peer memory (default), or NCCL all-reduce + replicated apply
     p2p_env = os.environ.get("CDAE_B200_P2P", "")
-    ctx.p2p = world > 1 and (p2p_env == "1" or args.allreduce == "p2p")
-    ctx.p2p_label = "NVLink peer-memory kernel"
+    ctx.p2p = world > 1 and args.allreduce != "nccl" and p2p_env != "0"
+    ctx.p2p_label = ("one kernel over NVLink peer memory: reduce-scatter by peer loads, the rank's slice of the AdaGrad step, "
+                     "all-gather of the updated parameters by peer stores")
 
     primary = args.config or "B"
     extras = []

@@ -490,7 +490,7 @@ static int combine_and_apply(cdae_handle* h) {
     fa.steps_off = (int64_t)(h->m.g_steps - h->m.gW);
     fa.steps_slot = 0;
     fa.lr = h->m.lr; fa.beta = h->m.beta; fa.lambda = h->m.lambda; fa.adagrad = h->m.adagrad;
-    p2p::fused_step_kernel<<<h->sm_count, 512, 0, h->stream>>>(fa);
+    p2p::fused_step_kernel<<<h->sm_count * 2, 512, 0, h->stream>>>(fa);   // 2 resident CTAs per SM: more NVLink loads in flight
     KERNEL_OK(h);
     h->p2p_parity ^= 1;
     point_item_side(h, h->grad.p + (size_t)h->p2p_parity * h->grad_floats);
@@ -992,24 +992,38 @@ int cdae_train_users(cdae_handle* h, const int64_t* uids, int64_t n, const uint8
   if (!h || !uids || n <= 0) return set_error(CDAE_E_INVALID, "need a non-empty uid list");
   TRY(begin_call(h));
   h->topn_k = 0;  // stored recommendation lists are stale
+  std::vector<int64_t> own_uids;
+  std::vector<uint8_t> own_keep;
+  std::vector<int32_t> own_negs;
   if (h->world > 1) {
-    // process group (collective; every rank passes the SAME arguments): rank r trains slice r of the list —
-    // the rule of build_plan — and the minibatch is combined like any other.  stats are this rank's part.
+    // process group (collective; every rank passes the SAME arguments): a rank trains the listed users it
+    // OWNS — the rule of build_plan; their Wu / Uu rows are current only there — and the minibatch is
+    // combined like any other.  stats are this rank's part.
     {
       std::vector<int64_t> sorted(uids, uids + n);
       std::sort(sorted.begin(), sorted.end());
       if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) return set_error(CDAE_E_INVALID, "uids must be distinct inside one frozen minibatch");
     }
-    const int64_t a = n * h->rank / h->world, b = n * (h->rank + 1) / h->world;
+    const int nu = h->cfg.num_neg;
     int64_t off = 0;
-    for (int64_t i = 0; i < a; ++i) {
-      if (uids[i] < 0 || uids[i] >= h->U) return set_error(CDAE_E_INVALID, "uid %lld outside [0,%lld)", (long long)uids[i], (long long)h->U);
-      off += h->row_ptr_h[uids[i] + 1] - h->row_ptr_h[uids[i]];
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t u = uids[i];
+      if (u < 0 || u >= h->U) return set_error(CDAE_E_INVALID, "uid %lld outside [0,%lld)", (long long)u, (long long)h->U);
+      const int64_t len = h->row_ptr_h[u + 1] - h->row_ptr_h[u];
+      const int64_t lo = (u / h->batch_users) * h->batch_users, nb = std::min<int64_t>(h->batch_users, h->U - lo);
+      const int64_t a = lo + nb * h->rank / h->world, b = lo + nb * (h->rank + 1) / h->world;
+      if (u >= a && u < b) {
+        own_uids.push_back(u);
+        if (keep_mask) own_keep.insert(own_keep.end(), keep_mask + off, keep_mask + off + len);
+        if (negatives) own_negs.insert(own_negs.end(), negatives + off * nu, negatives + (off + len) * nu);
+      }
+      off += len;
     }
-    uids += a;
-    n = b - a;
-    if (keep_mask) keep_mask += off;
-    if (negatives) negatives += off * h->cfg.num_neg;
+    // a rank that owns none of the listed users still takes part in the combine step
+    uids = own_uids.data();
+    n = (int64_t)own_uids.size();
+    if (keep_mask) { own_keep.push_back(0); keep_mask = own_keep.data(); }
+    if (negatives) { own_negs.push_back(0); negatives = own_negs.data(); }
   }
   int64_t slots = 0, n_in = 0, n_out = 0;
   TRY(stage_users(h, uids, n, true, &slots, &n_in, &n_out));

@@ -153,62 +153,79 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
 
   const int64_t lo = a.n4 * a.rank / a.world, hi = a.n4 * (a.rank + 1) / a.world;
   float* const my_params = a.params[a.rank];
-  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i >= a.bp_end && i < a.b_lo) continue;      // counts: no parameter behind them
-    if (i >= a.b_hi) continue;                      // steps / flag
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  // UN elements per thread and iteration, all peer loads issued before the first use: an NVLink round trip
+  // is ~2-3 us, so the loop must keep several 16-byte loads per peer in flight per thread
+  constexpr int UN = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * UN) {
+    float4 s[UN];
+    float cnt[UN];
+    bool on[UN];
 #pragma unroll
-    for (int p = 0; p < MAX_RANKS; ++p)
-      if (p < a.world) {
-        const float4 v = ld_sys_v4(a.grads[p] + i * 4);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-    float lin = 0.f;                                // coefficient of w in the gradient: lambda * (count | steps)
-    if (i < a.w_rows_end) {
-      if (a.lambda != 0.f) {
-        float c = 0.f;
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + u * stride;
+      // counts and steps have no parameter behind them
+      on[u] = i < hi && !(i >= a.bp_end && i < a.b_lo) && i < a.b_hi;
+      s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cnt[u] = 0.f;
+      if (!on[u]) continue;
+#pragma unroll
+      for (int p = 0; p < MAX_RANKS; ++p)
+        if (p < a.world) {                       // fixed rank order: the sum is a pure function of the G buffers
+          const float4 v = ld_sys_v4(a.grads[p] + i * 4);
+          s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
+        }
+      if (i < a.w_rows_end && a.lambda != 0.f) {
         const int64_t row = i / a.ld4;
 #pragma unroll
         for (int p = 0; p < MAX_RANKS; ++p)
-          if (p < a.world) c += ld_sys_f32(a.grads[p] + a.cnt_off + row);
-        lin = a.lambda * c;
+          if (p < a.world) cnt[u] += ld_sys_f32(a.grads[p] + a.cnt_off + row);
       }
-    } else if (i >= a.b_lo) {
-      lin = a.lambda * steps;
     }
-    if (discard) continue;
-    if (lin == 0.f && s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;   // untouched: identical everywhere already
-    const float4 w4 = *reinterpret_cast<const float4*>(my_params + i * 4);
-    float g[4] = {s.x, s.y, s.z, s.w};
-    float w[4] = {w4.x, w4.y, w4.z, w4.w};
-    if (lin != 0.f) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) g[k] += lin * w[k];
-    }
-    if (a.adagrad) {
-      const float4 a4 = *reinterpret_cast<const float4*>(a.acc + i * 4);
-      float ac[4] = {a4.x, a4.y, a4.z, a4.w};
+    for (int u = 0; u < UN; ++u) {
+      if (!on[u] || discard) continue;
+      const int64_t i = i0 + u * stride;
+      // coefficient of w in the gradient: lambda * (kept-input count of the row | user steps for b)
+      const float lin = i < a.w_rows_end ? a.lambda * cnt[u] : (i >= a.b_lo ? a.lambda * steps : 0.f);
+      const float4 sv = s[u];
+      if (lin == 0.f && sv.x == 0.f && sv.y == 0.f && sv.z == 0.f && sv.w == 0.f) continue;   // untouched: identical everywhere already
+      const float4 w4 = *reinterpret_cast<const float4*>(my_params + i * 4);
+      float g[4] = {sv.x, sv.y, sv.z, sv.w};
+      float w[4] = {w4.x, w4.y, w4.z, w4.w};
+      if (lin != 0.f) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (g[k] == 0.f) continue;                  // upd(0) is a no-op (and no 0/0 in pad columns when beta = 0)
-        ac[k] += g[k] * g[k];
-        g[k] = g[k] / (a.beta + sqrtf(ac[k]));
+        for (int k = 0; k < 4; ++k) g[k] += lin * w[k];
       }
-      *reinterpret_cast<float4*>(a.acc + i * 4) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+      if (a.adagrad) {
+        const float4 a4 = *reinterpret_cast<const float4*>(a.acc + i * 4);
+        float ac[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (g[k] == 0.f) continue;                  // upd(0) is a no-op (and no 0/0 in pad columns when beta = 0)
+          ac[k] += g[k] * g[k];
+          g[k] = g[k] / (a.beta + sqrtf(ac[k]));
+        }
+        *reinterpret_cast<float4*>(a.acc + i * 4) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
+      const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int p = 0; p < MAX_RANKS; ++p)
+        if (p < a.world) st_sys_v4(a.params[p] + i * 4, wn);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
-    const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
-#pragma unroll
-    for (int p = 0; p < MAX_RANKS; ++p)
-      if (p < a.world) st_sys_v4(a.params[p] + i * 4, wn);
   }
 
-  // last block out: "my stores are out" -> wait until everybody's are in
-  __threadfence_system();
+  // last block out: "my stores are out" -> wait until everybody's are in.  One system-scope fence per block,
+  // after the block barrier, orders every thread's stores (fence cumulativity — the grid.sync() pattern)
+  // before the counter increment; 75,000 per-thread MEMBAR.SYS would each wait for the NVLink acks.
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (last) {
     if (threadIdx.x == 0) *a.done = 0u;

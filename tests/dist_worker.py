@@ -156,7 +156,8 @@ def _run(rank, world, local, failures):
                     continue
                 err = np.abs(v - ref).max() / max(1e-12, np.abs(ref).max())
                 # full decode: three epochs of bf16 rounding flips (tests/test_gpu_fulldec.py) on top of fp32 order
-                if not err <= (3e-3 if full else 2e-4):
+                # (full-decode accumulators: sums of squared bf16-operand sums, 8e-3 as in tests/test_gpu_fulldec.py)
+                if not err <= ((8e-3 if k.endswith("_ag") else 3e-3) if full else 2e-4):
                     failures.append("%s%s%s %s: max err %.3g" % (kw, " p2p" if use_p2p else "", " sharded-csr" if sharded else "", k, err))
             keep = np.concatenate([o.sample_keep(7, 0x80000000, u) for u in range(U)])
             ref_loss = o.data_loss(keep)
