@@ -61,6 +61,24 @@ __device__ __forceinline__ float ld_sys_f32(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+// Bulk data of the fused step: weak accesses.  The peers' gradients are complete and unchanging once their
+// flag has been acquired (acquire + __syncthreads orders these loads after it; the L1 was invalidated at
+// kernel launch and every address is read once, so no stale line can be hit), and the stores are published
+// by the system-scope fence in front of the closing announcement.  STRONG.SYS accesses reached only
+// ~250 GB/s per direction on 8 GPUs (profiles/r02_c_*).
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer_v4(float* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void st_sys_v4(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -135,18 +153,23 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
     __threadfence_system();
     announce(a.flags, a.rank, a.world, a.epoch);
   }
-  // zero the gradient buffer the previous minibatch consumed while the announcements travel
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (int64_t)gridDim.x * blockDim.x)
-    *reinterpret_cast<float4*>(a.grad_next + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   wait_all(a.flags, a.rank, a.world, a.epoch);
 
-  // scalars every element may need: user steps of the minibatch (n * lambda * b) and the bad-CSR flag
+  // scalars every element may need: user steps of the minibatch (n * lambda * b) and the bad-CSR flag.  ONE
+  // thread per peer and block fetches them (every thread doing so made 10^5 - 10^6 requests for the same two
+  // words of each peer: the whole step ran at 40 GB/s on 8 GPUs, profiles/r02_c_*).
+  __shared__ float sc_s[2][MAX_RANKS];
+  if ((int)threadIdx.x < a.world) {
+    sc_s[0][threadIdx.x] = ld_sys_f32(a.grads[threadIdx.x] + a.steps_off + a.steps_slot);
+    sc_s[1][threadIdx.x] = ld_sys_f32(a.grads[threadIdx.x] + a.steps_off + 2);
+  }
+  __syncthreads();
   float steps = 0.f, bad = 0.f;
 #pragma unroll
   for (int p = 0; p < MAX_RANKS; ++p)
     if (p < a.world) {
-      steps += ld_sys_f32(a.grads[p] + a.steps_off + a.steps_slot);
-      bad += ld_sys_f32(a.grads[p] + a.steps_off + 2);
+      steps += sc_s[0][p];
+      bad += sc_s[1][p];
     }
   const bool discard = bad != 0.f;
   if (discard && blockIdx.x == 0 && threadIdx.x == 0) *a.bad_csr_out = 1;
@@ -172,14 +195,14 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
 #pragma unroll
       for (int p = 0; p < MAX_RANKS; ++p)
         if (p < a.world) {                       // fixed rank order: the sum is a pure function of the G buffers
-          const float4 v = ld_sys_v4(a.grads[p] + i * 4);
+          const float4 v = ld_peer_v4(a.grads[p] + i * 4);
           s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
         }
       if (i < a.w_rows_end && a.lambda != 0.f) {
         const int64_t row = i / a.ld4;
 #pragma unroll
         for (int p = 0; p < MAX_RANKS; ++p)
-          if (p < a.world) cnt[u] += ld_sys_f32(a.grads[p] + a.cnt_off + row);
+          if (p < a.world) cnt[u] += ld_peer_f32(a.grads[p] + a.cnt_off + row);
       }
     }
 #pragma unroll
@@ -213,9 +236,12 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
       const float4 wn = make_float4(w[0], w[1], w[2], w[3]);
 #pragma unroll
       for (int p = 0; p < MAX_RANKS; ++p)
-        if (p < a.world) st_sys_v4(a.params[p] + i * 4, wn);
+        if (p < a.world) st_peer_v4(a.params[p] + i * 4, wn);
     }
   }
+  // zero the gradient buffer the PREVIOUS minibatch consumed (local; overlaps the NVLink stores in flight)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (int64_t)gridDim.x * blockDim.x)
+    *reinterpret_cast<float4*>(a.grad_next + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // last block out: "my stores are out" -> wait until everybody's are in.  One system-scope fence per block,
   // after the block barrier, orders every thread's stores (fence cumulativity — the grid.sync() pattern)
