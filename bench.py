@@ -314,8 +314,11 @@ def measure(name, ctx, args, primary):
                 box = [None] * world
                 dist.all_gather_object(box, b)
                 return box
-            m.dist_p2p_init(gather)
-            allreduce = ctx.p2p_label
+            if args.allreduce in ("auto", "nvls") and os.environ.get("CDAE_B200_NVLS", "1") != "0" and m.dist_mc_init(rank, world, gather):
+                allreduce = ctx.nvls_label
+            else:
+                m.dist_p2p_init(gather)
+                allreduce = ctx.p2p_label
     m.init_params(SEED)
     rp_pin, col_pin = m.pinned_array(rp), m.pinned_array(col)
     steps = args.steps if primary else max(3, min(args.steps, 5))
@@ -530,6 +533,8 @@ def run_ours(args):
     # the combine step: one fused kernel over NVLink peer memory (default), or NCCL all-reduce + replicated apply
     p2p_env = os.environ.get("CDAE_B200_P2P", "")
     ctx.p2p = world > 1 and args.allreduce != "nccl" and p2p_env != "0"
+    ctx.nvls_label = ("one kernel through the NVSwitch multicast engine (NVLS): multimem.ld_reduce of the rank's gradient slice, its slice "
+                      "of the AdaGrad step, multimem.st of the updated parameters")
     ctx.p2p_label = ("one kernel over NVLink peer memory: reduce-scatter by peer loads, the rank's slice of the AdaGrad step, "
                      "all-gather of the updated parameters by peer stores")
 
@@ -605,7 +610,8 @@ def main():
     ap.add_argument("--extra", default=None, help="comma list of further configurations to add under `configs`")
     ap.add_argument("--no-extra", action="store_true", help="only the primary configuration")
     ap.add_argument("--batch-users", type=int, default=0, help="config B: users per minibatch per GPU (default 8192)")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p"])
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p", "nvls"],
+                    help="combine step: auto = NVLS kernel where multicast is available, else the peer-memory kernel")
     ap.add_argument("--cpu-sample", type=int, default=30000,
                     help="users in the bounded CPU-baseline sample (about 10-15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

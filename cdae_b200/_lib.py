@@ -70,9 +70,13 @@ SIGNATURES = {
     "cdae_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "cdae_dist_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cdae_dist_p2p_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cdae_dist_mc_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "cdae_dist_mc_attach": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cdae_dist_mc_bind": (C.c_int, [C.c_void_p]),
     "cdae_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "cdae_profile_get": (C.c_int, [C.c_void_p, f64p, i64p]),
     "cdae_probe_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, f64p, f64p]),
+    "cdae_debug_combine": (C.c_int, [C.c_void_p, C.c_int32]),
     "cdae_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "cdae_host_free": (C.c_int, [C.c_void_p]),
     "cdae_synchronize": (C.c_int, [C.c_void_p]),

@@ -414,6 +414,7 @@ static SampleArgs make_sample_args(cdae_handle* h, uint64_t seed, uint32_t pass)
 }
 
 static int run_fulldec(cdae_handle* h, const BatchDev& bt);   // fulldec_api.inl
+static void mc_release(cdae_handle* h);                       // mc_nvls.inl
 static int combine_and_apply(cdae_handle* h);
 
 // gather -> activate -> decode -> hidden_backward -> scatter -> [all-reduce] -> apply
@@ -462,6 +463,40 @@ static int combine_and_apply(cdae_handle* h) {
   // CDAE_B200_DEBUG_SKIP_ALLREDUCE=1: measurement aid only (ranks diverge) — isolates the cost of
   // the collective in a scaling run
   static const bool skip_allreduce = getenv("CDAE_B200_DEBUG_SKIP_ALLREDUCE") != nullptr;
+  if (h->world > 1 && !skip_allreduce && h->p2p_on && h->mc_active) {
+    // NVLS: the same fused step through the switch's multicast engine (p2p::mc_step_kernel)
+    ProfScope ps(h, CDAE_K_ALLREDUCE);
+    p2p::McArgs ma;
+    const size_t cur = (size_t)h->p2p_parity * h->grad_floats, nxt = (size_t)(h->p2p_parity ^ 1) * h->grad_floats;
+    float* mc_params = reinterpret_cast<float*>(h->mc_mc + 4096);
+    ma.mc_grad = mc_params + h->grad_floats + cur;
+    ma.mc_params = mc_params;
+    ma.mc_flags = reinterpret_cast<uint32_t*>(h->mc_mc);
+    ma.flags = reinterpret_cast<const uint32_t*>(h->mc_uc);
+    ma.params = h->item_params.p;
+    ma.acc = h->item_acc.p;
+    ma.grad_next = h->grad.p + nxt;
+    ma.done = h->p2p_done;
+    ma.bad_csr_out = &h->stats_d->bad_csr;
+    ma.rank = h->rank; ma.world = h->world;
+    ma.target = (uint32_t)h->world * (++h->p2p_epoch);
+    ma.n4 = (int64_t)(h->grad_floats / 4);
+    const int64_t ld4 = h->ld / 4, rows4 = h->I * ld4;
+    ma.w_rows_end = rows4;
+    ma.w_end = rows4 * (h->m.asym ? 2 : 1);
+    ma.bp_end = ma.w_end + h->I4 / 4;
+    ma.b_lo = ma.bp_end + 2 * (h->I4 / 4);
+    ma.b_hi = ma.b_lo + ld4;
+    ma.ld4 = (int)ld4;
+    ma.cnt_off = (int64_t)(h->m.gcnt - h->m.gW);
+    ma.steps_off = (int64_t)(h->m.g_steps - h->m.gW);
+    ma.lr = h->m.lr; ma.beta = h->m.beta; ma.lambda = h->m.lambda; ma.adagrad = h->m.adagrad;
+    p2p::mc_step_kernel<<<h->sm_count * 2, 512, 0, h->stream>>>(ma);
+    KERNEL_OK(h);
+    h->p2p_parity ^= 1;
+    point_item_side(h, h->grad.p + (size_t)h->p2p_parity * h->grad_floats);
+    return 0;
+  }
   if (h->world > 1 && !skip_allreduce && h->p2p_on && h->p2p_fused) {
     ProfScope ps(h, CDAE_K_ALLREDUCE);
     p2p::FusedArgs fa;
@@ -708,6 +743,7 @@ int cdae_destroy(cdae_handle* h) {
     if (h->p2p_flags[r]) cudaIpcCloseMemHandle(h->p2p_flags[r]);
   }
   if (h->p2p_my_flags) cudaFree(h->p2p_my_flags);
+  mc_release(h);   // NVLS mode: the item-side buffers belong to a VMM block, not to cudaMalloc
   ModelDev& m = h->m;
   float* tabs[] = {m.Wu, m.Uu, m.Wu_ag, m.Uu_ag};
   for (float* p : tabs) if (p) cudaFree(p);
@@ -1187,6 +1223,7 @@ static int p2p_prepare(cdae_handle* h) {
     h->grad.cap = 2 * h->grad_floats;
     h->p2p_parity = 0;
     h->m.steps_slot = 0;
+    h->m.direct_lambda = 1;
     point_item_side(h, h->grad.p);
   }
   CU(cudaMalloc(&h->p2p_my_flags, 64 * sizeof(uint32_t)));
@@ -1311,6 +1348,20 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
   return 0;
 }
 
+// Measurement aid: the combine step alone (no user work in front of it, so no rank skew): `reps` times
+// "fill the current gradient buffer with a non-zero pattern, combine_and_apply".  With cdae_profile on,
+// cdae_profile_get's allreduce / apply classes then hold the pure cost of the step.  Collective.
+int cdae_debug_combine(cdae_handle* h, int32_t reps) {
+  if (!h || reps <= 0) return set_error(CDAE_E_INVALID, "bad argument");
+  TRY(begin_call(h));
+  for (int r = 0; r < reps; ++r) {
+    // 0x2f2f2f2f = 1.59e-10f: every element has a (tiny) gradient, so every parameter is rewritten and published
+    CU(cudaMemsetAsync(h->m.gW, 0x2f, sizeof(float) * (size_t)(h->m.gcnt - h->m.gW), h->stream));
+    TRY(combine_and_apply(h));
+  }
+  return end_call(h, nullptr);
+}
+
 int cdae_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes < 0) return set_error(CDAE_E_INVALID, "bad argument");
   CU(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
@@ -1350,3 +1401,4 @@ static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users
 #include "topn_api.inl"
 #include "fulldec_api.inl"
 #include "dataset.inl"
+#include "mc_nvls.inl"

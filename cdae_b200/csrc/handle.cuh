@@ -52,6 +52,12 @@ struct cdae_handle {
   uint32_t* p2p_my_flags = nullptr;
   unsigned int* p2p_done = nullptr;
   int p2p_parity = 0;              // which gradient buffer the current minibatch accumulates into
+  // NVLS mode (mc_nvls.inl): the item side lives in a VMM block bound to a multicast object
+  bool mc_creator = false, mc_attached = false, mc_active = false;
+  unsigned long long mc_handle = 0, mc_phys = 0;   // CUmemGenericAllocationHandle
+  size_t mc_size = 0;
+  char* mc_uc = nullptr;           // this rank's block (unicast mapping): [flags 4 KB | parameters | gradients x2]
+  char* mc_mc = nullptr;           // the same offsets through the multicast mapping
   uint32_t p2p_epoch = 0;
   int sm_count = 148;
   size_t dev_bytes = 0;

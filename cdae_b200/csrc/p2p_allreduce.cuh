@@ -180,9 +180,9 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
   // is ~2-3 us, so the loop must keep several 16-byte loads per peer in flight per thread
   constexpr int UN = 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * UN) {
+  bool first_pass = true;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 - (int64_t)threadIdx.x - (int64_t)blockIdx.x * blockDim.x < hi; i0 += stride * UN) {
     float4 s[UN];
-    float cnt[UN];
     bool on[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -190,7 +190,6 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
       // counts and steps have no parameter behind them
       on[u] = i < hi && !(i >= a.bp_end && i < a.b_lo) && i < a.b_hi;
       s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      cnt[u] = 0.f;
       if (!on[u]) continue;
 #pragma unroll
       for (int p = 0; p < MAX_RANKS; ++p)
@@ -198,19 +197,19 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
           const float4 v = ld_peer_v4(a.grads[p] + i * 4);
           s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
         }
-      if (i < a.w_rows_end && a.lambda != 0.f) {
-        const int64_t row = i / a.ld4;
-#pragma unroll
-        for (int p = 0; p < MAX_RANKS; ++p)
-          if (p < a.world) cnt[u] += ld_peer_f32(a.grads[p] + a.cnt_off + row);
-      }
+    }
+    if (first_pass) {
+      // zero the gradient buffer the PREVIOUS minibatch consumed while the peer loads above are in flight
+      first_pass = false;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride)
+        *reinterpret_cast<float4*>(a.grad_next + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       if (!on[u] || discard) continue;
       const int64_t i = i0 + u * stride;
-      // coefficient of w in the gradient: lambda * (kept-input count of the row | user steps for b)
-      const float lin = i < a.w_rows_end ? a.lambda * cnt[u] : (i >= a.b_lo ? a.lambda * steps : 0.f);
+      // coefficient of w in the gradient: lambda * user steps for b (item rows: scatter_kernel added lambda*W[j] itself)
+      const float lin = i >= a.b_lo ? a.lambda * steps : 0.f;
       const float4 sv = s[u];
       if (lin == 0.f && sv.x == 0.f && sv.y == 0.f && sv.z == 0.f && sv.w == 0.f) continue;   // untouched: identical everywhere already
       const float4 w4 = *reinterpret_cast<const float4*>(my_params + i * 4);
@@ -239,9 +238,6 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
         if (p < a.world) st_peer_v4(a.params[p] + i * 4, wn);
     }
   }
-  // zero the gradient buffer the PREVIOUS minibatch consumed (local; overlaps the NVLink stores in flight)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (int64_t)gridDim.x * blockDim.x)
-    *reinterpret_cast<float4*>(a.grad_next + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // last block out: "my stores are out" -> wait until everybody's are in.  One system-scope fence per block,
   // after the block barrier, orders every thread's stores (fence cumulativity — the grid.sync() pattern)
@@ -258,6 +254,141 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
     __threadfence_system();
     announce(a.flags, a.rank, a.world, a.epoch + 1);
     wait_all(a.flags, a.rank, a.world, a.epoch + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The same combine step through the NVSwitch's multicast engine (NVLS; host side in mc_nvls.inl).  Every
+// rank's [flags | parameters | gradients x2] block is bound at offset 0 of one multicast object, so
+//   multimem.ld_reduce  sums a word over all ranks INSIDE THE SWITCH: the rank pulls its 1/G slice once
+//                       (1/G of the buffer inbound per GPU instead of (G-1)/G),
+//   multimem.st         stores the updated parameters into every rank's copy with one outbound write,
+//   multimem.red        increments every rank's barrier counter.
+// NVLink traffic per GPU and minibatch drops from 2 * (G-1)/G * N bytes to 2 * N/G.
+__device__ __forceinline__ float4 mc_ld_sum_v4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ float mc_ld_sum_f32(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st_v4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_red_add_release(uint32_t* mc, uint32_t v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
+
+struct McArgs {
+  const float* mc_grad;            // multicast address of the CURRENT gradient buffer
+  float* mc_params;                // multicast address of the item-side parameter buffer
+  uint32_t* mc_flags;              // multicast address of the barrier counters ([0] gradients complete, [1] stores out)
+  const uint32_t* flags;           // this rank's own counters (unicast)
+  const float* params;             // this rank's parameters (unicast)
+  float* acc;                      // this rank's accumulator buffer (only its slice is kept current)
+  float* grad_next;                // this rank's OTHER gradient buffer: zeroed here
+  unsigned int* done;
+  int* bad_csr_out;
+  int rank, world;
+  uint32_t target;                 // world * (minibatches so far): the value both counters reach when everyone arrived
+  int64_t n4;
+  int64_t w_rows_end, w_end, bp_end, b_lo, b_hi;
+  int ld4;
+  int64_t cnt_off, steps_off;
+  float lr, beta, lambda;
+  int adagrad;
+};
+
+__device__ __forceinline__ void mc_wait(const uint32_t* counter, uint32_t target) {
+  if (threadIdx.x == 0)
+    while ((int32_t)(ld_acquire_sys(counter) - target) < 0) {}
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
+  // stream order: every kernel that added to this rank's gradients has finished
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    mc_red_add_release(a.mc_flags + 0, 1u);
+  }
+  mc_wait(a.flags + 0, a.target);
+  __shared__ float sc_s[2];
+  if (threadIdx.x < 2) sc_s[threadIdx.x] = mc_ld_sum_f32(a.mc_grad + a.steps_off + (threadIdx.x == 0 ? 0 : 2));
+  __syncthreads();
+  const float steps = sc_s[0];
+  const bool discard = sc_s[1] != 0.f;
+  if (discard && blockIdx.x == 0 && threadIdx.x == 0) *a.bad_csr_out = 1;
+
+  const int64_t lo = a.n4 * a.rank / a.world, hi = a.n4 * (a.rank + 1) / a.world;
+  constexpr int UN = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool first_pass = true;
+  // (the loop bound is block-uniform: every thread takes part in the zeroing of the first pass)
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 - (int64_t)threadIdx.x - (int64_t)blockIdx.x * blockDim.x < hi; i0 += stride * UN) {
+    float4 s[UN];
+    bool on[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + u * stride;
+      on[u] = i < hi && !(i >= a.bp_end && i < a.b_lo) && i < a.b_hi;
+      s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!on[u]) continue;
+      s[u] = mc_ld_sum_v4(a.mc_grad + i * 4);
+    }
+    if (first_pass) {
+      // zero the gradient buffer the PREVIOUS minibatch consumed while the switch reductions are in flight
+      first_pass = false;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride)
+        *reinterpret_cast<float4*>(a.grad_next + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!on[u] || discard) continue;
+      const int64_t i = i0 + u * stride;
+      const float lin = i >= a.b_lo ? a.lambda * steps : 0.f;   // item rows: scatter_kernel added lambda*W[j] itself
+      const float4 sv = s[u];
+      if (lin == 0.f && sv.x == 0.f && sv.y == 0.f && sv.z == 0.f && sv.w == 0.f) continue;
+      const float4 w4 = *reinterpret_cast<const float4*>(a.params + i * 4);
+      float g[4] = {sv.x, sv.y, sv.z, sv.w};
+      float w[4] = {w4.x, w4.y, w4.z, w4.w};
+      if (lin != 0.f) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[k] += lin * w[k];
+      }
+      if (a.adagrad) {
+        const float4 a4 = *reinterpret_cast<const float4*>(a.acc + i * 4);
+        float ac[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (g[k] == 0.f) continue;
+          ac[k] += g[k] * g[k];
+          g[k] = g[k] / (a.beta + sqrtf(ac[k]));
+        }
+        *reinterpret_cast<float4*>(a.acc + i * 4) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
+      mc_st_v4(a.mc_params + i * 4, make_float4(w[0], w[1], w[2], w[3]));
+    }
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) {
+      *a.done = 0u;
+      __threadfence_system();
+      mc_red_add_release(a.mc_flags + 1, 1u);
+    }
+    mc_wait(a.flags + 1, a.target);
   }
 }
 

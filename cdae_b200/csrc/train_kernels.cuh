@@ -41,6 +41,8 @@ struct ModelDev {
   float lambda, lr, beta, scale;  // scale = scaled ? 1/(1-q) : 1   (cdae.hpp:202-205)
   int loss, nu;
   int adagrad, asym, user_factor, linear, tanh_act, linear_function;
+  int direct_lambda;  // 1: scatter_kernel adds lambda*W[j] itself (reads the row) instead of counting occurrences for
+                      // the optimiser pass — process groups: the fused combine step then needs no per-row counts
 };
 
 struct BatchDev {
@@ -570,7 +572,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
   const int32_t* items = bt.col + wi.s0;
   const uint8_t* keep = bt.keep + wi.aux0;
   float* cnt = m.gcnt + (int64_t)m.steps_slot * m.I4;
-  const bool count = m.lambda != 0.f;
+  const bool count = m.lambda != 0.f && !m.direct_lambda;
+  const bool direct = m.lambda != 0.f && m.direct_lambda;
   float4 d[NV], sd[NV], gu[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -604,7 +607,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int c = RM::col4(gl, v);
-        if (c < m.K) red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, sd[v]);
+        if (c < m.K) {
+          float4 add = sd[v];
+          if (direct) add = fma4(m.lambda, ld4(m.W + (int64_t)it[t] * m.ld + c), add);
+          red_add_v4(m.gW + (int64_t)it[t] * m.ld + c, add);
+        }
       }
       if (count && gl == 0) red_add_f32(cnt + it[t], 1.f);
     }

@@ -288,6 +288,50 @@ class CDAE:
         tb = C.create_string_buffer(table, len(table))
         _lib.check(self._L.cdae_dist_p2p_open(self._h, tb))
 
+    def dist_mc_init(self, rank, world, all_gather):
+        """Switch the combine step to the NVLS kernel (NVSwitch multicast, cdae_dist_mc_*).  `all_gather(obj)
+        -> list in rank order` is the caller's collective.  Returns False — with nothing changed — where
+        multicast is unavailable, so the caller can fall back to dist_p2p_init / NCCL; all ranks agree."""
+        import os
+        import socket
+        fd, ok, srv, path = -1, True, None, None
+        if rank == 0:
+            v = C.c_int32(-1)
+            rc = self._L.cdae_dist_mc_create(self._h, C.byref(v))
+            ok, fd = rc == 0, v.value
+            if ok:
+                path = "/tmp/cdae_mc_%d.sock" % os.getpid()
+                if os.path.exists(path):
+                    os.unlink(path)
+                srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                srv.bind(path)
+                srv.listen(world)
+        ok, path = all_gather((ok, path))[0]
+        if not ok:
+            return False
+        if rank == 0:
+            for _ in range(world - 1):                       # the multicast object travels as a file descriptor
+                conn, _a = srv.accept()
+                socket.send_fds(conn, [b"mc"], [fd])
+                conn.close()
+            srv.close()
+            os.unlink(path)
+        else:
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(path)
+            _msg, fds, _f, _a = socket.recv_fds(c, 16, 1)
+            c.close()
+            fd = fds[0]
+        rc = self._L.cdae_dist_mc_attach(self._h, fd)
+        if not all(all_gather(rc == 0)):
+            raise CdaeError(rc, "cdae_dist_mc_attach failed on some rank: " + self._L.cdae_last_error().decode("utf-8", "replace"))
+        rc = self._L.cdae_dist_mc_bind(self._h)              # (the all_gather above was the barrier "everyone attached")
+        if not all(all_gather(rc == 0)):
+            raise CdaeError(rc, "cdae_dist_mc_bind failed on some rank: " + self._L.cdae_last_error().decode("utf-8", "replace"))
+        if rank != 0:
+            os.close(fd)
+        return True
+
     def save(self, path):
         """Versioned binary checkpoint of every parameter block incl. AdaGrad state (cdae_save)."""
         _lib.check(self._L.cdae_save(self._h, str(path).encode()))

@@ -242,6 +242,23 @@ int cdae_dist_init(cdae_handle* h, int32_t rank, int32_t world, const void* nccl
 int cdae_dist_p2p_export(cdae_handle* h, void* record256_out);
 int cdae_dist_p2p_open(cdae_handle* h, const void* all_handles);
 
+/* NVLS mode of the same fused combine step (csrc/mc_nvls.inl, p2p::mc_step_kernel): the item-side
+ * buffers of every rank are bound to ONE NVSwitch multicast object; the kernel sums a rank's slice of the
+ * gradients with multimem.ld_reduce (reduced inside the switch: 1/G of the buffer inbound per GPU instead
+ * of (G-1)/G), applies its slice of the optimiser step and publishes the updated parameters with
+ * multimem.st.  Use INSTEAD of cdae_dist_p2p_export / _open, after cdae_dist_init:
+ *   rank 0:     cdae_dist_mc_create  -> a POSIX file descriptor of the multicast object; the caller passes
+ *               it to the other ranks (SCM_RIGHTS over a unix socket; cdae_b200/model.py has a helper)
+ *   every rank: cdae_dist_mc_attach(fd)   (rank 0 passes the descriptor it created, or -1)
+ *   -- caller's barrier: every rank has attached --
+ *   every rank: cdae_dist_mc_bind          (allocates, binds and maps the rank's block, moves the item side)
+ *   -- caller's barrier --                 then train.
+ * Each returns CDAE_E_STATE where multicast is unavailable (no NVSwitch, driver without NVLS, device
+ * attribute MULTICAST_SUPPORTED = 0): fall back to cdae_dist_p2p_* or plain NCCL. */
+int cdae_dist_mc_create(cdae_handle* h, int32_t* fd_out);
+int cdae_dist_mc_attach(cdae_handle* h, int32_t fd);
+int cdae_dist_mc_bind(cdae_handle* h);
+
 /* Per-kernel-class device timing for benchmarks: when enabled, every kernel launch is
  * bracketed by CUDA events on the handle's stream; cdae_profile_get returns, per class,
  * the summed milliseconds and the number of launches since cdae_profile(h, 1). */
@@ -264,6 +281,11 @@ int cdae_profile_get(cdae_handle* h, double* ms_out /*[CDAE_K_COUNT]*/,
  * and returns bytes moved per second (GB/s) and the average launch time over `reps` launches. */
 int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits, int32_t reps,
                   double* gbs_out, double* ms_out);
+
+/* Measurement aid: the per-minibatch combine step alone, `reps` times on a synthetic non-zero gradient
+ * (collective in a process group; with cdae_profile on, the allreduce / apply classes hold its pure
+ * device time — no user work in front of it, hence no rank skew).  Parameters drift by ~1e-10 per call. */
+int cdae_debug_combine(cdae_handle* h, int32_t reps);
 
 /* pinned host memory for buffers that cross the boundary every step */
 int cdae_host_alloc(void** ptr, int64_t bytes);

@@ -64,12 +64,17 @@ def _run(rank, world, local, failures):
                dict(loss="SQUARE", asymmetric=True, num_dim=20, p2p=True),
                dict(loss="CE", using_adagrad=False, learn_rate=0.02, num_dim=33, p2p=True),
                dict(loss="CE", beta=1.0, asymmetric=True, num_dim=100, full_decode=True, p2p=True),
+               # the same fused step through the NVSwitch multicast engine (skipped where NVLS is unavailable)
+               dict(loss="CE", beta=1.0, num_dim=50, nvls=True),
+               dict(loss="SQUARE", asymmetric=True, num_dim=20, nvls=True),
+               dict(loss="CE", beta=1.0, asymmetric=True, num_dim=100, full_decode=True, nvls=True),
                # every rank holds only the rows of the users it trains (the others are empty in its CSR)
                dict(loss="CE", beta=1.0, num_dim=50, p2p=True, sharded_csr=True),
                dict(loss="CE", beta=1.0, num_dim=50, sharded_csr=True)):
         kw = dict(kw)
         full = kw.pop("full_decode", False)
         use_p2p = kw.pop("p2p", False)
+        use_mc = kw.pop("nvls", False)
         sharded = kw.pop("sharded_csr", False)
         cfg = orc.default_config(**kw)
         data = cases.small_dataset(U=403, I=500, mean=12.0, seed=5)
@@ -88,11 +93,17 @@ def _run(rank, world, local, failures):
         uid = [CDAE.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         m.dist_init(rank, world, uid[0])
+        def gather(b):
+            box = [None] * world
+            dist.all_gather_object(box, b)
+            return box
+        if use_mc:
+            if not m.dist_mc_init(rank, world, gather):
+                if rank == 0:
+                    print("dist_worker: NVLS unavailable here (%s) - case skipped" % kw, flush=True)
+                m.close()
+                continue
         if use_p2p:
-            def gather(b):
-                box = [None] * world
-                dist.all_gather_object(box, b)
-                return box
             m.dist_p2p_init(gather)
         m.set_params(p)
         steps = 0
@@ -158,7 +169,7 @@ def _run(rank, world, local, failures):
                 # full decode: three epochs of bf16 rounding flips (tests/test_gpu_fulldec.py) on top of fp32 order
                 # (full-decode accumulators: sums of squared bf16-operand sums, 8e-3 as in tests/test_gpu_fulldec.py)
                 if not err <= ((8e-3 if k.endswith("_ag") else 3e-3) if full else 2e-4):
-                    failures.append("%s%s%s %s: max err %.3g" % (kw, " p2p" if use_p2p else "", " sharded-csr" if sharded else "", k, err))
+                    failures.append("%s%s%s%s %s: max err %.3g" % (kw, " p2p" if use_p2p else "", " nvls" if use_mc else "", " sharded-csr" if sharded else "", k, err))
             keep = np.concatenate([o.sample_keep(7, 0x80000000, u) for u in range(U)])
             ref_loss = o.data_loss(keep)
             if loss is not None and not abs(loss - ref_loss) <= (2e-3 if full else 2e-4) * abs(ref_loss):
