@@ -5,5 +5,5 @@ Python here is the test / benchmark mirror of the C++ host class in cdae_b200/ho
 thin callers of the C ABI in include/cdae_b200.h, implemented by hand-written sm_100a kernels
 in cdae_b200/csrc/."""
 from ._lib import CdaeError  # noqa: F401
-from .model import CDAE, CDAEConfig  # noqa: F401
+from .model import CDAE, CDAEConfig, CDAEGroup  # noqa: F401
 from .data import Dataset  # noqa: F401

@@ -73,6 +73,24 @@ SIGNATURES = {
     "cdae_dist_mc_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "cdae_dist_mc_attach": (C.c_int, [C.c_void_p, C.c_int32]),
     "cdae_dist_mc_bind": (C.c_int, [C.c_void_p]),
+    "cdae_group_create": (C.c_int, [C.POINTER(Config), C.c_int64, C.c_int64, i64p, i32p, i32p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cdae_group_destroy": (C.c_int, [C.c_void_p]),
+    "cdae_group_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "cdae_group_handle": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cdae_group_init_params": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "cdae_group_set_param": (C.c_int, [C.c_void_p, C.c_int, f64p, C.c_int64]),
+    "cdae_group_get_param": (C.c_int, [C.c_void_p, C.c_int, f64p, C.c_int64]),
+    "cdae_group_get_param_rows": (C.c_int, [C.c_void_p, C.c_int, i64p, C.c_int64, f64p]),
+    "cdae_group_train_epoch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(EpochStats)]),
+    "cdae_group_train_epoch_csr": (C.c_int, [C.c_void_p, i64p, i32p, C.c_uint64, C.c_int64, C.POINTER(EpochStats)]),
+    "cdae_group_train_users": (C.c_int, [C.c_void_p, i64p, C.c_int64, u8p, i32p, C.POINTER(EpochStats)]),
+    "cdae_group_encode": (C.c_int, [C.c_void_p, i64p, C.c_int64, u8p, C.c_double, f32p]),
+    "cdae_group_data_loss": (C.c_int, [C.c_void_p, C.c_uint64, f64p]),
+    "cdae_group_penalty_loss": (C.c_int, [C.c_void_p, f64p]),
+    "cdae_group_topn_build": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cdae_group_topn_lookup": (C.c_int, [C.c_void_p, C.c_int64, i64p, f32p]),
+    "cdae_group_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cdae_group_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cdae_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "cdae_profile_get": (C.c_int, [C.c_void_p, f64p, i64p]),
     "cdae_probe_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, f64p, f64p]),

@@ -3,6 +3,7 @@
 // topn_kernels.cuh on one stream, and (optionally) all-reduces the dense gradients with NCCL.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -602,6 +603,9 @@ static int end_call(cdae_handle* h, cdae_epoch_stats_t* stats) {
     stats->h2d_bytes = h->h2d;
     stats->d2h_bytes = h->d2h;
   }
+  if (h->stats_h->bad_csr == 2)
+    return set_error(CDAE_E_STATE, "a peer GPU did not reach the combine step within %d s (its process or thread failed?); "
+                     "the parameters of this call are undefined", (int)(p2p::SPIN_LIMIT_NS / 1000000000ull));
   if (h->stats_h->bad_csr) h->csr_bad = true;
   if (h->stats_h->bad_csr)
     return set_error(CDAE_E_INVALID, "the CSR passed to cdae_train_epoch_csr has an item id outside [0,%lld) or a row that is "
@@ -1402,3 +1406,4 @@ static int topn_candidates(cdae_handle* h, const float* Wd, const int32_t* users
 #include "fulldec_api.inl"
 #include "dataset.inl"
 #include "mc_nvls.inl"
+#include "group.inl"

@@ -54,6 +54,7 @@ struct cdae_handle {
   int p2p_parity = 0;              // which gradient buffer the current minibatch accumulates into
   // NVLS mode (mc_nvls.inl): the item side lives in a VMM block bound to a multicast object
   bool mc_creator = false, mc_attached = false, mc_active = false;
+  bool mc_shared = false;          // the multicast object handle belongs to another handle of this process (cdae_group)
   unsigned long long mc_handle = 0, mc_phys = 0;   // CUmemGenericAllocationHandle
   size_t mc_size = 0;
   char* mc_uc = nullptr;           // this rank's block (unicast mapping): [flags 4 KB | parameters | gradients x2]

@@ -199,6 +199,6 @@ static void mc_release(cdae_handle* h) {
     g_mc.MemAddressFree((CUdeviceptr)h->mc_uc, h->mc_size);
     g_mc.MemRelease((CUmemGenericAllocationHandle)h->mc_phys);
   }
-  if (h->mc_handle) g_mc.MemRelease((CUmemGenericAllocationHandle)h->mc_handle);
+  if (h->mc_handle && !h->mc_shared) g_mc.MemRelease((CUmemGenericAllocationHandle)h->mc_handle);
   h->mc_active = h->mc_attached = false;
 }

@@ -87,10 +87,27 @@ __device__ __forceinline__ void st_sys_v4(float* p, float4 v) {
 __device__ __forceinline__ void announce(uint32_t* const* flags, int rank, int world, uint32_t epoch) {
   if ((int)threadIdx.x < world) st_release_sys(flags[threadIdx.x] + rank, epoch);
 }
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// A peer that never arrives (its process failed before the combine step) must not hang this GPU: the spin
+// gives up after SPIN_LIMIT_NS and raises *timeout_flag = 2 (reported by the host as CDAE_E_STATE; the
+// parameters of this call are then undefined).
+constexpr uint64_t SPIN_LIMIT_NS = 20ull * 1000 * 1000 * 1000;
 // every calling block waits until all ranks announced `epoch` to this rank
-__device__ __forceinline__ void wait_all(uint32_t* const* flags, int rank, int world, uint32_t epoch) {
-  if ((int)threadIdx.x < world)
-    while ((int32_t)(ld_acquire_sys(flags[rank] + threadIdx.x) - epoch) < 0) {}
+__device__ __forceinline__ void wait_all(uint32_t* const* flags, int rank, int world, uint32_t epoch,
+                                         int* timeout_flag = nullptr) {
+  if ((int)threadIdx.x < world) {
+    const uint64_t t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(flags[rank] + threadIdx.x) - epoch) < 0) {
+      if (global_ns() - t0 > SPIN_LIMIT_NS) {
+        if (timeout_flag) *timeout_flag = 2;
+        break;
+      }
+    }
+  }
   __syncthreads();
 }
 
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
     __threadfence_system();
     announce(a.flags, a.rank, a.world, a.epoch);
   }
-  wait_all(a.flags, a.rank, a.world, a.epoch);
+  wait_all(a.flags, a.rank, a.world, a.epoch, a.bad_csr_out);
 
   // scalars every element may need: user steps of the minibatch (n * lambda * b) and the bad-CSR flag.  ONE
   // thread per peer and block fetches them (every thread doing so made 10^5 - 10^6 requests for the same two
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
     if (threadIdx.x == 0) *a.done = 0u;
     __threadfence_system();
     announce(a.flags, a.rank, a.world, a.epoch + 1);
-    wait_all(a.flags, a.rank, a.world, a.epoch + 1);
+    wait_all(a.flags, a.rank, a.world, a.epoch + 1, a.bad_csr_out);
   }
 }
 
@@ -303,9 +320,16 @@ struct McArgs {
   int adagrad;
 };
 
-__device__ __forceinline__ void mc_wait(const uint32_t* counter, uint32_t target) {
-  if (threadIdx.x == 0)
-    while ((int32_t)(ld_acquire_sys(counter) - target) < 0) {}
+__device__ __forceinline__ void mc_wait(const uint32_t* counter, uint32_t target, int* timeout_flag) {
+  if (threadIdx.x == 0) {
+    const uint64_t t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(counter) - target) < 0) {
+      if (global_ns() - t0 > SPIN_LIMIT_NS) {
+        *timeout_flag = 2;
+        break;
+      }
+    }
+  }
   __syncthreads();
 }
 
@@ -315,7 +339,7 @@ __global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
     __threadfence_system();
     mc_red_add_release(a.mc_flags + 0, 1u);
   }
-  mc_wait(a.flags + 0, a.target);
+  mc_wait(a.flags + 0, a.target, a.bad_csr_out);
   __shared__ float sc_s[2];
   if (threadIdx.x < 2) sc_s[threadIdx.x] = mc_ld_sum_f32(a.mc_grad + a.steps_off + (threadIdx.x == 0 ? 0 : 2));
   __syncthreads();
@@ -388,7 +412,7 @@ __global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
       __threadfence_system();
       mc_red_add_release(a.mc_flags + 1, 1u);
     }
-    mc_wait(a.flags + 1, a.target);
+    mc_wait(a.flags + 1, a.target, a.bad_csr_out);
   }
 }
 

@@ -65,6 +65,8 @@ struct CDAEConfig {
   size_t batch_users = 0;
   int device = -1;
   bool full_decode = false;   // decode against ALL items on tcgen05 (num_neg ignored); env CDAE_B200_FULL_DECODE=1
+  int num_gpus = 1;           // > 1: one process drives that many GPUs (cdae_group_*, users sharded data-parallel,
+                              // batch_users is then the GLOBAL minibatch); env CDAE_B200_GPUS
 };
 
 class CDAE : public RecsysModelBase {
@@ -75,6 +77,7 @@ class CDAE : public RecsysModelBase {
     if (const char* e = std::getenv("CDAE_B200_BATCH_USERS")) mcfg_.batch_users = std::strtoull(e, nullptr, 10);
     if (const char* e = std::getenv("CDAE_B200_DEVICE")) mcfg_.device = std::atoi(e);
     if (const char* e = std::getenv("CDAE_B200_FULL_DECODE")) mcfg_.full_decode = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CDAE_B200_GPUS")) mcfg_.num_gpus = std::max(1, std::atoi(e));
     LOG(INFO) << "CDAE (cdae_b200, ABI " << cdae_abi_version() << ") Configure: \n"
         << "\t{lambda: " << mcfg_.lambda << "}, "
         << "{Loss: " << loss_->loss_type() << "}, "
@@ -101,14 +104,15 @@ class CDAE : public RecsysModelBase {
   // cdae.hpp:78-101 — sum over users of the loss of their positives under a fresh corruption
   double data_loss(const Data& data_set, size_t sample_size = 0) const {
     double v = 0.;
-    check(cdae_data_loss(handle(), seed_ + 0x9E3779B97F4A7C15ull * (uint64_t)(++st_->loss_calls), &v));
+    const uint64_t s = seed_ + 0x9E3779B97F4A7C15ull * (uint64_t)(++st_->loss_calls);
+    check(st_->g ? cdae_group_data_loss(st_->g, s, &v) : cdae_data_loss(handle(), s, &v));
     return v;
   }
 
   // cdae.hpp:103-107
   double penalty_loss() const {
     double v = 0.;
-    check(cdae_penalty_loss(handle(), &v));
+    check(st_->g ? cdae_group_penalty_loss(st_->g, &v) : cdae_penalty_loss(handle(), &v));
     return v;
   }
 
@@ -147,16 +151,27 @@ class CDAE : public RecsysModelBase {
     c.device = mcfg_.device < 0 ? 0 : mcfg_.device;
     c.full_decode = mcfg_.full_decode ? 1 : 0;
     cdae_handle* h = nullptr;
-    check(cdae_create(&c, (int64_t)num_users_, (int64_t)num_items_, row_ptr.data(), col.data(), &h));
+    cdae_group* g = nullptr;
+    if (mcfg_.num_gpus > 1) {
+      // one process, several GPUs: devices c.device .. c.device + num_gpus - 1
+      std::vector<int32_t> devs((size_t)mcfg_.num_gpus);
+      for (int d = 0; d < mcfg_.num_gpus; ++d) devs[(size_t)d] = c.device + d;
+      check(cdae_group_create(&c, (int64_t)num_users_, (int64_t)num_items_, row_ptr.data(), col.data(), devs.data(),
+                              (int32_t)devs.size(), &g));
+      check(cdae_group_handle(g, 0, &h));
+    } else {
+      check(cdae_create(&c, (int64_t)num_users_, (int64_t)num_items_, row_ptr.data(), col.data(), &h));
+    }
     st_ = std::make_shared<State>();
     st_->h = h;
+    st_->g = g;
     st_->row_ptr = std::move(row_ptr);
     st_->col = std::move(col);
     // the reference draws W, V, Wu with Eigen's Random(), i.e. from rand() (cdae.hpp:112-121):
     // take the engine's stream seed from rand() too, so srand() still decides the run
     seed_ = ((uint64_t)(uint32_t)rand() << 32) ^ (uint64_t)(uint32_t)rand();
     if (const char* e = std::getenv("CDAE_B200_SEED")) seed_ = std::strtoull(e, nullptr, 10);
-    check(cdae_init_params(h, seed_));
+    check(g ? cdae_group_init_params(g, seed_) : cdae_init_params(h, seed_));
     epoch_ = 0;
   }
 
@@ -164,7 +179,7 @@ class CDAE : public RecsysModelBase {
   // as in the reference, which also ignores `train_data` here)
   void train_one_iteration(const Data& train_data) {
     cdae_epoch_stats_t s;
-    check(cdae_train_epoch(handle(), seed_, epoch_++, &s));
+    check(st_->g ? cdae_group_train_epoch(st_->g, seed_, epoch_++, &s) : cdae_train_epoch(handle(), seed_, epoch_++, &s));
     st_->last = s;
     st_->topn_k = 0;  // lists are stale now
   }
@@ -180,7 +195,8 @@ class CDAE : public RecsysModelBase {
       ids.resize(b - a);
       z.resize((b - a) * K);
       for (size_t u = a; u < b; ++u) ids[u - a] = (int64_t)u;
-      check(cdae_encode(handle(), ids.data(), (int64_t)ids.size(), nullptr, 1.0, z.data()));
+      check(st_->g ? cdae_group_encode(st_->g, ids.data(), (int64_t)ids.size(), nullptr, 1.0, z.data())
+                   : cdae_encode(handle(), ids.data(), (int64_t)ids.size(), nullptr, 1.0, z.data()));
       for (size_t u = a; u < b; ++u)
         for (size_t k = 0; k < K; ++k) user_vec(u, k) = z[(u - a) * K + k];
     }
@@ -207,7 +223,8 @@ class CDAE : public RecsysModelBase {
       if (st_->topn_k != (int)topk) build_lists((int)topk);
     }
     std::vector<int64_t> ids(topk);
-    check(cdae_topn_lookup(handle(), (int64_t)uid, ids.data(), nullptr));
+    check(st_->g ? cdae_group_topn_lookup(st_->g, (int64_t)uid, ids.data(), nullptr)
+                 : cdae_topn_lookup(handle(), (int64_t)uid, ids.data(), nullptr));
     std::vector<size_t> ret(topk);
     for (size_t i = 0; i < topk; ++i) ret[i] = (size_t)ids[i];
     return ret;
@@ -232,7 +249,8 @@ class CDAE : public RecsysModelBase {
     for (auto& j : negs) j = (int32_t)sample_negative_item(output_set);
     const int64_t u = (int64_t)uid;
     cdae_epoch_stats_t s;
-    check(cdae_train_users(handle(), &u, 1, keep.data(), negs.data(), &s));
+    check(st_->g ? cdae_group_train_users(st_->g, &u, 1, keep.data(), negs.data(), &s)
+                 : cdae_train_users(handle(), &u, 1, keep.data(), negs.data(), &s));
     st_->topn_k = 0;
   }
 
@@ -260,7 +278,8 @@ class CDAE : public RecsysModelBase {
     CHECK_EQ(kept, item_set.size()) << "cdae_b200: item_set must be a subset of the user's train items";
     std::vector<float> z(mcfg_.num_dim);
     const int64_t u = (int64_t)uid;
-    check(cdae_encode(handle(), &u, 1, keep.data(), scale, z.data()));
+    check(st_->g ? cdae_group_encode(st_->g, &u, 1, keep.data(), scale, z.data())
+                 : cdae_encode(handle(), &u, 1, keep.data(), scale, z.data()));
     DVector h2(mcfg_.num_dim);
     for (size_t k = 0; k < mcfg_.num_dim; ++k) h2(k) = z[k];
     return h2;
@@ -279,7 +298,14 @@ class CDAE : public RecsysModelBase {
   }
 
   // ---- additions (no reference counterpart) ----
-  cdae_handle* engine() const { return handle(); }
+  cdae_handle* engine() const { return handle(); }       // (GPU 0's handle in multi-GPU mode)
+  cdae_group* engine_group() const { return st_ ? st_->g : nullptr; }
+  // model checkpoint incl. AdaGrad state (the reference can only save Data, io/serialize.hpp:16-46)
+  void save(const std::string& path) const { check(st_->g ? cdae_group_save(st_->g, path.c_str()) : cdae_save(handle(), path.c_str())); }
+  void load(const std::string& path) {
+    check(st_->g ? cdae_group_load(st_->g, path.c_str()) : cdae_load(handle(), path.c_str()));
+    st_->topn_k = 0;
+  }
   const cdae_epoch_stats_t& last_epoch_stats() const { return st_->last; }
   // TOPN_Evaluation::evaluate (evaluation.hpp:113-181) on the device, for callers that hold the
   // test set as CSR: out8 = P@1,P@5,P@10,R@1,R@5,R@10,MAP@5,MAP@10
@@ -291,6 +317,7 @@ class CDAE : public RecsysModelBase {
     }
     std::vector<double> out(8);
     int64_t n = 0;
+    CHECK(!st_->g) << "cdae_b200: evaluate_topn is single-GPU; in multi-GPU mode TOPN_Evaluation reads the lists through recommend()";
     check(cdae_topn_evaluate(handle(), test_row_ptr.data(), test_col.data(), out.data(), &n));
     return out;
   }
@@ -299,14 +326,18 @@ class CDAE : public RecsysModelBase {
   static constexpr int kDefaultTopk = 10;  // the list length TOPN_Evaluation asks for (evaluation.hpp:145)
 
   struct State {
-    cdae_handle* h = nullptr;
+    cdae_handle* h = nullptr;   // the engine (GPU 0's handle in multi-GPU mode: owned by g)
+    cdae_group* g = nullptr;    // multi-GPU mode
     std::vector<int64_t> row_ptr;
     std::vector<int32_t> col;
     std::mutex mu;
     int topn_k = 0;
     uint64_t loss_calls = 0;
     cdae_epoch_stats_t last{};
-    ~State() { if (h) cdae_destroy(h); }
+    ~State() {
+      if (g) cdae_group_destroy(g);
+      else if (h) cdae_destroy(h);
+    }
   };
 
   cdae_handle* handle() const {
@@ -317,7 +348,7 @@ class CDAE : public RecsysModelBase {
     if (rc != 0) LOG(FATAL) << "cdae_b200 error " << rc << ": " << cdae_last_error();
   }
   void build_lists(int topk) const {
-    check(cdae_topn_build(handle(), topk));
+    check(st_->g ? cdae_group_topn_build(st_->g, topk) : cdae_topn_build(handle(), topk));
     st_->topn_k = topk;
   }
 

@@ -370,3 +370,116 @@ class CDAE:
 
     def synchronize(self):
         _lib.check(self._L.cdae_synchronize(self._h))
+
+
+class CDAEGroup(CDAE):
+    """`class CDAE` on several GPUs of ONE process (cdae_group_*, csrc/group.inl): one engine handle per
+    device, users sharded like a process group, one worker thread per GPU inside every call.
+    config.batch_users is the GLOBAL minibatch (0 -> 8192 per GPU)."""
+
+    def __init__(self, config=None, devices=(0, 1)):
+        super().__init__(config)
+        self.devices = list(devices)
+        self._g = C.c_void_p()
+
+    def reset(self, U, I, row_ptr, col):
+        self.close()
+        self.U, self.I = int(U), int(I)
+        self.row_ptr = _arr(row_ptr, np.int64)
+        self.col = _arr(col, np.int32)
+        c = self.config.to_c()
+        dev = _arr(self.devices, np.int32)
+        _lib.check(self._L.cdae_group_create(C.byref(c), self.U, self.I, _ptr(self.row_ptr, _lib.i64p), _ptr(self.col, _lib.i32p),
+                                             _ptr(dev, _lib.i32p), len(dev), C.byref(self._g)))
+        h = C.c_void_p()
+        _lib.check(self._L.cdae_group_handle(self._g, 0, C.byref(h)))
+        self._h = h                      # GPU 0's handle: shapes, replicated item-side reads, profiling
+        return self
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._L.cdae_group_destroy(self._g)
+            self._g = C.c_void_p()
+        self._h = C.c_void_p()
+
+    def init_params(self, seed):
+        self._topk = 0
+        _lib.check(self._L.cdae_group_init_params(self._g, seed))
+
+    def set_params(self, params):
+        self._topk = 0
+        for k, v in params.items():
+            r, c = self.param_shape(k)
+            if r * c == 0:
+                continue
+            a = _arr(np.asarray(v, np.float64).reshape(-1), np.float64)
+            _lib.check(self._L.cdae_group_set_param(self._g, PARAM_ID[k], _ptr(a, _lib.f64p), a.size))
+
+    def get_param(self, name):
+        r, c = self.param_shape(name)
+        a = np.zeros(r * c)
+        if a.size:
+            _lib.check(self._L.cdae_group_get_param(self._g, PARAM_ID[name], _ptr(a, _lib.f64p), a.size))
+        return a.reshape(r, c) if c > 1 else a
+
+    def train_one_iteration(self, seed=0, epoch=0, csr=None):
+        st = EpochStats()
+        if csr is None:
+            _lib.check(self._L.cdae_group_train_epoch(self._g, seed, epoch, C.byref(st)))
+        else:
+            rp, cl = _arr(csr[0], np.int64), _arr(csr[1], np.int32)
+            _lib.check(self._L.cdae_group_train_epoch_csr(self._g, _ptr(rp, _lib.i64p), _ptr(cl, _lib.i32p), seed, epoch, C.byref(st)))
+        self.last_stats = st
+        self._topk = 0
+        return st
+
+    def train_users(self, uids, keep_mask, negatives):
+        u, k = _arr(uids, np.int64), _arr(keep_mask, np.uint8)
+        n = None if negatives is None else _arr(negatives, np.int32)
+        st = EpochStats()
+        _lib.check(self._L.cdae_group_train_users(self._g, _ptr(u, _lib.i64p), len(u), _ptr(k, _lib.u8p),
+                                                  None if n is None else _ptr(n, _lib.i32p), C.byref(st)))
+        self._topk = 0
+        return st
+
+    def encode(self, uids, keep_mask=None, scale=1.0):
+        u = _arr(uids, np.int64)
+        z = np.zeros((len(u), self.config.num_dim), np.float32)
+        k = None if keep_mask is None else _arr(keep_mask, np.uint8)
+        _lib.check(self._L.cdae_group_encode(self._g, _ptr(u, _lib.i64p), len(u), None if k is None else _ptr(k, _lib.u8p),
+                                             scale, _ptr(z, _lib.f32p)))
+        return z
+
+    def data_loss(self, seed=0):
+        v = C.c_double()
+        _lib.check(self._L.cdae_group_data_loss(self._g, seed, C.byref(v)))
+        return v.value
+
+    def penalty_loss(self):
+        v = C.c_double()
+        _lib.check(self._L.cdae_group_penalty_loss(self._g, C.byref(v)))
+        return v.value
+
+    def pre_recommend(self, topk=10):
+        _lib.check(self._L.cdae_group_topn_build(self._g, topk))
+        self._topk = topk
+
+    def recommend(self, uid, topk=10):
+        if self._topk != topk:
+            self.pre_recommend(topk)
+        ids, sc = np.zeros(topk, np.int64), np.zeros(topk, np.float32)
+        _lib.check(self._L.cdae_group_topn_lookup(self._g, uid, _ptr(ids, _lib.i64p), _ptr(sc, _lib.f32p)))
+        return ids, sc
+
+    def recommend_all(self, topk=10):
+        ids, sc = np.zeros((self.U, topk), np.int64), np.zeros((self.U, topk), np.float32)
+        for u in range(self.U):
+            ids[u], sc[u] = self.recommend(u, topk)
+        return ids, sc
+
+    def save(self, path):
+        _lib.check(self._L.cdae_group_save(self._g, str(path).encode()))
+
+    def load(self, path):
+        _lib.check(self._L.cdae_group_load(self._g, str(path).encode()))
+        self._topk = 0

@@ -259,6 +259,39 @@ int cdae_dist_mc_create(cdae_handle* h, int32_t* fd_out);
 int cdae_dist_mc_attach(cdae_handle* h, int32_t fd);
 int cdae_dist_mc_bind(cdae_handle* h);
 
+/* ---- single-process multi-GPU mode (csrc/group.inl) -------------------------------------------------
+ * The reference's app is one process (Solver<CDAE>::train, solver-inl.hpp:19,53,55).  A cdae_group owns
+ * one engine handle per device and drives them from one worker thread per GPU inside every call, wired
+ * like a process group of `n` ranks (same user sharding, same fused combine step over peer memory —
+ * NVLS where available — with NCCL for the read-backs), so libcf::CDAE can use the whole box:
+ * cdae_b200/host/model/recsys/cdae.hpp switches to it with CDAE_B200_GPUS=n.  cfg->batch_users is the
+ * GLOBAL minibatch (0 -> 8192 per GPU); devices NULL -> 0..n-1.  Every cdae_group_X is the collective
+ * form of cdae_X; cdae_group_topn_lookup (thread-safe) and cdae_group_encode route each user to the
+ * GPU that trains it.  cdae_group_handle exposes one GPU's handle, e.g. for item-side (replicated) reads. */
+typedef struct cdae_group cdae_group;
+int cdae_group_create(const cdae_config_t* cfg, int64_t num_users, int64_t num_items, const int64_t* row_ptr,
+                      const int32_t* col_idx, const int32_t* devices, int32_t n, cdae_group** out);
+int cdae_group_destroy(cdae_group* g);
+int cdae_group_size(cdae_group* g, int32_t* n);
+int cdae_group_handle(cdae_group* g, int32_t rank, cdae_handle** out);
+int cdae_group_init_params(cdae_group* g, uint64_t seed);
+int cdae_group_set_param(cdae_group* g, int which, const double* src, int64_t n);
+int cdae_group_get_param(cdae_group* g, int which, double* dst, int64_t n);
+int cdae_group_get_param_rows(cdae_group* g, int which, const int64_t* rows, int64_t n, double* dst);
+int cdae_group_train_epoch(cdae_group* g, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats);
+int cdae_group_train_epoch_csr(cdae_group* g, const int64_t* row_ptr, const int32_t* col_idx, uint64_t seed,
+                               int64_t epoch, cdae_epoch_stats_t* stats);
+int cdae_group_train_users(cdae_group* g, const int64_t* uids, int64_t n, const uint8_t* keep_mask,
+                           const int32_t* negatives, cdae_epoch_stats_t* stats);
+int cdae_group_encode(cdae_group* g, const int64_t* uids, int64_t n, const uint8_t* keep_mask, double scale,
+                      float* z_out);
+int cdae_group_data_loss(cdae_group* g, uint64_t seed, double* out);
+int cdae_group_penalty_loss(cdae_group* g, double* out);
+int cdae_group_topn_build(cdae_group* g, int32_t topk);
+int cdae_group_topn_lookup(cdae_group* g, int64_t uid, int64_t* ids_out, float* scores_out);
+int cdae_group_save(cdae_group* g, const char* path);
+int cdae_group_load(cdae_group* g, const char* path);
+
 /* Per-kernel-class device timing for benchmarks: when enabled, every kernel launch is
  * bracketed by CUDA events on the handle's stream; cdae_profile_get returns, per class,
  * the summed milliseconds and the number of launches since cdae_profile(h, 1). */
