@@ -307,6 +307,7 @@ static BatchDev make_batch(cdae_handle* h, const WorkItem* in, int64_t n_in, con
   bt.H = h->acc3.p; bt.HG = h->acc3.p + per; bt.GU = h->acc3.p + 2 * per;
   bt.Z = h->zd.p; bt.D = h->zd.p + per;
   bt.flags = 0;
+  bt.ch_in = h->ch_in;
   return bt;
 }
 
@@ -346,6 +347,25 @@ static int launch_gather(cdae_handle* h, const BatchDev& bt, const SampleArgs* s
   } else {
     SampleArgs none{};
 #define CALL(G, NV) gather_kernel<G, NV, false><<<grid, 256, 0, h->stream>>>(h->m, bt, none, st)
+    DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  }
+  KERNEL_OK(h);
+  return 0;
+}
+// H3 + H4 in one kernel for the epoch path (encode_fused_kernel): mode 1 = register-direct row loads,
+// 2 = rows staged in shared memory by cp.async.bulk.  Users with more than one input chunk are finished
+// by activate_kernel (bt.flags carries BATCH_FUSED_ENCODE so it skips the others).
+static int launch_encode_fused(cdae_handle* h, const BatchDev& bt, const SampleArgs& sa, int mode) {
+  if (bt.n_in_items == 0) return 0;
+  ProfScope ps(h, CDAE_K_GATHER);
+  const int grid = cdiv((int64_t)bt.n_in_items * 32, 256);
+  if (mode == 2) {
+#define CALL(G, NV) encode_fused_kernel<G, NV, true><<<grid, 256, 0, h->stream>>>(h->m, bt, sa, h->stats_d, h->m.scale)
+    DISPATCH_LD(h->ld, CALL);
+#undef CALL
+  } else {
+#define CALL(G, NV) encode_fused_kernel<G, NV, false><<<grid, 256, 0, h->stream>>>(h->m, bt, sa, h->stats_d, h->m.scale)
     DISPATCH_LD(h->ld, CALL);
 #undef CALL
   }
@@ -419,10 +439,22 @@ static void mc_release(cdae_handle* h);                       // mc_nvls.inl
 static int combine_and_apply(cdae_handle* h);
 
 // gather -> activate -> decode -> hidden_backward -> scatter -> [all-reduce] -> apply
-static int run_train_minibatch(cdae_handle* h, const BatchDev& bt, const SampleArgs* sa) {
+static int run_train_minibatch(cdae_handle* h, const BatchDev& bt_in, const SampleArgs* sa) {
   const size_t per = (size_t)std::max<int64_t>(h->scratch_users, 1) * h->ld;
   CU(cudaMemsetAsync(h->acc3.p, 0, sizeof(float) * per * (h->m.linear_function ? 3 : 2), h->stream));
-  TRY(launch_gather(h, bt, sa, true));
+  // CDAE_B200_ENCODE: split (gather_kernel + activate_kernel, default) | fused | tma — the A/B of the
+  // north-star encode (profiles/r02_e_*); only the epoch path (device-side sampling) has the fused forms
+  static const int enc_mode = [] {
+    const char* e = getenv("CDAE_B200_ENCODE");
+    return !e ? 0 : strcmp(e, "fused") == 0 ? 1 : strcmp(e, "tma") == 0 ? 2 : 0;
+  }();
+  BatchDev bt = bt_in;
+  if (sa && enc_mode != 0) {
+    bt.flags |= BATCH_FUSED_ENCODE;
+    TRY(launch_encode_fused(h, bt, *sa, h->ld <= 64 ? enc_mode : 1));   // (the staged form exists for ld <= 64)
+  } else {
+    TRY(launch_gather(h, bt, sa, true));
+  }
   TRY(launch_activate(h, bt, h->m.scale));
   if (h->cfg.full_decode) {
     TRY(run_fulldec(h, bt));

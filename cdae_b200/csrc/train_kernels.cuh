@@ -55,10 +55,11 @@ struct BatchDev {
   uint8_t* keep;              // [minibatch slots]       1 = input item survives corruption
   const int32_t* negs;        // [minibatch slots * nu]  explicit negatives (unsampled mode only)
   float *H, *Z, *HG, *D, *GU;  // [n_users][ld]
+  int ch_in;                  // slots per input chunk (64)
   int flags;                  // BATCH_BY_UID: rows of H / Z are indexed by GLOBAL uid (whole-table
                               // encode); BATCH_KEEP_ALL: no corruption mask, every input item is kept
 };
-enum { BATCH_BY_UID = 1, BATCH_KEEP_ALL = 2 };
+enum { BATCH_BY_UID = 1, BATCH_KEEP_ALL = 2, BATCH_FUSED_ENCODE = 4 };
 
 // Counter-based sampling parameters (same specification as oracle/cdae_oracle.h).
 struct SampleArgs {
@@ -275,6 +276,131 @@ __global__ void __launch_bounds__(256) gather_kernel(ModelDev m, BatchDev bt, Sa
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The north-star form of the encode (H3 + H4 in ONE kernel): corrupt, gather-reduce, bias, user row,
+// activation.  One warp per input chunk.  A user whose whole row is one chunk (<= 64 items: ~93 % of the
+// users at config B) is finished here and its z is stored; longer rows still add into H and are finished
+// by activate_kernel (which skips the users this kernel completed: BATCH_FUSED_ENCODE).
+//   TMA = false: rows go straight from L2 into the registers that sum them (gather_kernel's loads);
+//   TMA = true : the kept rows are STAGED IN SHARED MEMORY by bulk asynchronous copies (cp.async.bulk,
+//                one per row, issued by up to 32 lanes at once, completion on the warp's mbarrier) and
+//                summed from there — "TMA-staged W rows in shared memory, warp-shuffle reductions along K".
+// A/B at config B in profiles/r02_e_*; api.cu selects with CDAE_B200_ENCODE = split | fused | tma.
+constexpr int ENC_STAGE_ROWS = 16;   // rows staged per pass and warp (TMA = true; static shared memory: ld <= 64 only)
+__device__ __forceinline__ void mbar_init_w(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_w(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+template <int G, int NV, bool TMA>
+__global__ void __launch_bounds__(256) encode_fused_kernel(ModelDev m, BatchDev bt, SampleArgs sa, StatsDev* stats, float scale) {
+  using RM = RowMap<G, NV>;
+  constexpr int NG = RM::NG, UNR = RM::UNR, LD = 4 * G * NV;
+  __shared__ int32_t kept_s[8][64];
+  constexpr bool STAGED = TMA && LD <= 64;     // 8 warps x 16 rows x 256 B = 32 KB of static shared memory
+  __shared__ __align__(128) float stage_s[STAGED ? 8 : 1][STAGED ? ENC_STAGE_ROWS : 1][STAGED ? LD : 4];
+  __shared__ uint64_t bar_s[8];
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+  if (STAGED) {
+    if (lane == 0) mbar_init_w(&bar_s[wib], 1);
+    __syncwarp();
+  }
+  if (warp >= bt.n_in_items) return;
+  const WorkItem wi = load_item(bt.in_items + warp);
+  const int32_t* items = bt.col + wi.s0;
+  uint8_t* keep = bt.keep + wi.aux0;
+  int kept = sample_keep_chunk(wi, sa, keep, lane);
+  kept = (int)group_sum<32>((float)kept);
+  if (lane == 0 && kept) atomicAdd(&stats->inputs_kept[warp % STAT_STRIPES], (unsigned long long)kept);
+  __syncwarp();
+  // compact the kept item ids (ballot + prefix): the row loop then has no holes
+  int32_t* mine = kept_s[wib];
+  int nk = 0;
+  for (int b0 = 0; b0 < wi.n; b0 += 32) {
+    const int r = b0 + lane;
+    const bool k = r < wi.n && keep[r];
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (k) mine[nk + __popc(bal & ((1u << lane) - 1u))] = __ldg(items + r);
+    nk += __popc(bal);
+  }
+  __syncwarp();
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+  if (!STAGED) {
+    for (int base = 0; base < nk; base += NG * UNR) {
+      float4 w[UNR][NV];
+#pragma unroll
+      for (int t = 0; t < UNR; ++t) {
+        const int r = base + t * NG + grp;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          w[t][v] = (r < nk && RM::col4(gl, v) < m.K) ? ld4(m.W + (int64_t)mine[r < nk ? r : 0] * LD + RM::col4(gl, v)) : f4zero();
+      }
+#pragma unroll
+      for (int t = 0; t < UNR; ++t)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = add4(acc[v], w[t][v]);
+    }
+  } else {
+    const uint32_t row_bytes = (uint32_t)((m.K * 4 + 15) / 16 * 16);
+    uint32_t phase = 0;
+    for (int base = 0; base < nk; base += ENC_STAGE_ROWS) {
+      const int nr = min(ENC_STAGE_ROWS, nk - base);
+      if (lane == 0) mbar_expect_tx_w(&bar_s[wib], row_bytes * (uint32_t)nr);
+      __syncwarp();
+      if (lane < nr) bulk_g2s(&stage_s[wib][lane][0], m.W + (int64_t)mine[base + lane] * LD, row_bytes, &bar_s[wib]);
+      mbar_wait_w(&bar_s[wib], phase);
+      phase ^= 1u;
+      for (int r = grp; r < nr; r += NG)
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (RM::col4(gl, v) < m.K) acc[v] = add4(acc[v], *reinterpret_cast<const float4*>(&stage_s[wib][r][RM::col4(gl, v)]));
+      __syncwarp();   // the staging rows are overwritten by the next pass
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = cross_group_sum<G>(acc[v]);
+  const bool whole_row = wi.first && (int64_t)wi.n == __ldg(bt.row_ptr + wi.uid + 1) - __ldg(bt.row_ptr + wi.uid);
+  if (grp != 0) return;
+  if (!whole_row) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) red_add_v4(bt.H + (int64_t)wi.u_local * LD + RM::col4(gl, v), acc[v]);
+    return;
+  }
+  // the whole user is in this warp: bias, user row, activation (cdae.hpp:382-414)
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = RM::col4(gl, v);
+    float4 h = scale4(scale, acc[v]);
+    if (m.linear_function) h = mul4(ld4(m.Uu + (int64_t)wi.uid * LD + c), h);
+    h = add4(h, ld4(m.b + c));
+    if (m.user_factor) h = add4(h, ld4(m.Wu + (int64_t)wi.uid * LD + c));
+    float x[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!m.linear) x[i] = m.tanh_act ? act_tanh(x[i]) : act_sigmoid(x[i]);
+      if (c + i >= m.K) x[i] = 0.f;
+    }
+    st4(bt.Z + (int64_t)wi.u_local * LD + c, make_float4(x[0], x[1], x[2], x[3]));
+  }
+}
+
 // H4 second half, cdae.hpp:382-414: z = act([Uu (.)] scale*H + b [+ Wu[u]]); pad columns -> 0.
 __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, float scale) {
   const int ld4n = m.ld / 4;
@@ -282,6 +408,8 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
   if (idx >= (int64_t)bt.n_users * ld4n) return;
   const int u = (int)(idx / ld4n), c = (int)(idx % ld4n) * 4;
   const int64_t uid = bt.uids[u];
+  // users encode_fused_kernel finished (their whole row was one input chunk) already have their z
+  if ((bt.flags & BATCH_FUSED_ENCODE) && bt.row_ptr[uid + 1] - bt.row_ptr[uid] <= bt.ch_in) return;
   const int64_t zrow = (bt.flags & BATCH_BY_UID) ? uid : (int64_t)u;
   float4 h = scale4(scale, ld4(bt.H + zrow * m.ld + c));
   if (m.linear_function) h = mul4(ld4(m.Uu + uid * m.ld + c), h);
@@ -307,12 +435,16 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
 // Resident CTAs per SM the register allocation must allow, and row batches in flight per warp.  The kernel
 // is latency-bound (dependent chain LDS -> LDG -> dot -> shuffles -> SFU -> RED), so occupancy beats
 // per-warp unrolling: measured at config B (profiles/r02_b_*) UNR 4 / 3 CTAs 104.6 us per 8,192 users,
-// UNR 2 / 4 CTAs 100.4, UNR 1 / 5 CTAs 99.4, UNR 2 / 5 CTAs (spills) 118.7, UNR 4 / 2 CTAs 119.1.
+// UNR 2 / 4 CTAs 100.4, UNR 1 / 5 CTAs 99.4, UNR 2 / 5 CTAs (spills) 118.7, UNR 4 / 2 CTAs 119.1; with the
+// hand-pipelined loop (DECODE_PIPE) UNR 1 / 4 CTAs 95.6, UNR 2 / 3 CTAs 102.6.
 #ifndef DECODE_MIN_BLOCKS
 #define DECODE_MIN_BLOCKS 0  // 0 = by geometry: 4 for NV <= 2, else 3
 #endif
+#ifndef DECODE_PIPE
+#define DECODE_PIPE 1      // 1: loads of the next row batch are issued before the current batch is scored (see decode_kernel)
+#endif
 #ifndef DECODE_UNR
-#define DECODE_UNR 0       // row batches in flight per warp; 0 = by geometry: 4 for NV = 1, 2 for NV = 2, 3, 1 for NV = 4 (no spills at the register cap)
+#define DECODE_UNR 0       // row batches in flight per warp; 0 = by geometry (pipelined: 2 for NV = 1, else 1 — two batches live in registers)
 #endif
 constexpr int DECODE_MAX_NEGS = 96;  // ch_out * num_neg <= 96 by construction (api.cu)
 constexpr int DECODE_MAX_ROWS = 96;  // outputs of one chunk: n * (1 + num_neg) <= 96
@@ -373,7 +505,8 @@ template <int G, int NV, bool TRAIN, bool SAMPLED, int LT>
 __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS > 0 ? DECODE_MIN_BLOCKS : (NV <= 2 ? 4 : 3))
     decode_kernel(ModelDev m, BatchDev bt, SampleArgs sa, StatsDev* stats) {
   using RM = RowMap<G, NV>;
-  constexpr int NG = RM::NG, UNR = DECODE_UNR > 0 ? DECODE_UNR : (NV == 1 ? 4 : NV <= 3 ? 2 : 1), LD = 4 * G * NV;
+  constexpr int NG = RM::NG, UNR = DECODE_UNR > 0 ? DECODE_UNR : (DECODE_PIPE ? (NV == 1 ? 2 : 1) : (NV == 1 ? 4 : NV <= 3 ? 2 : 1)), LD = 4 * G * NV;
+  constexpr bool PIPE = DECODE_PIPE && NV <= 3;   // NV = 4: two batches of 4 float4 per lane do not fit the register cap
   constexpr int LIST = DECODE_MAX_ROWS + 1 + NG * UNR;   // (num_neg = 96: 97 rows) + one batch of slack
   __shared__ int32_t rows_s[8][LIST];    // the chunk's outputs: positives, then negatives
   __shared__ float lam_s[8][LIST];       // lambda of each output's row term (0 for a merged positive)
@@ -427,18 +560,22 @@ __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS > 0 ? DECODE_MIN_BLOCKS
   int bad = 0;
   const int first = gl == 0;
 
-  for (int base = 0; base < R; base += NG * UNR) {
-    int id[UNR];
+  // The row loop is software-pipelined by hand: the loads of batch i + 1 (ids from shared memory, rows and
+  // b' from L2) are issued BEFORE batch i is scored and reduced.  The reductions are `asm volatile` with a
+  // memory clobber, which the compiler will not move loads across, so without this every batch waited out
+  // its own L2 round trip (ncu r02_f: long_scoreboard 6.8 of ~12 stalled warps per issue).
+  constexpr int STEP = NG * UNR;
+  auto fetch = [&](int base, int (&id)[UNR], float4 (&w)[UNR][NV], float (&bp)[UNR]) {
 #pragma unroll
     for (int t = 0; t < UNR; ++t) id[t] = mine[base + t * NG + grp];
-    float4 w[UNR][NV];
-    float bp[UNR];
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) w[t][v] = ld4(Wl + (int64_t)id[t] * LD + v * G * 4);   // pad pieces read zeros
       bp[t] = __ldg(m.bp + id[t]);
     }
+  };
+  auto score = [&](int base, const int (&id)[UNR], const float4 (&w)[UNR][NV], const float (&bp)[UNR]) {
     float y[UNR];
 #pragma unroll
     for (int t = 0; t < UNR; ++t) {
@@ -473,6 +610,28 @@ __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS > 0 ? DECODE_MIN_BLOCKS
         else red_add_v4_if(grow + v * G * 4, gr, last_live);
       }
       red_add_f32_if(m.gbp + id[t], ok * fmaf(lambda, bp[t], g), first);
+    }
+  };
+  if constexpr (PIPE) {
+    int idA[UNR], idB[UNR];
+    float4 wA[UNR][NV], wB[UNR][NV];
+    float bpA[UNR], bpB[UNR];
+    fetch(0, idA, wA, bpA);
+    for (int base = 0; base < R; base += 2 * STEP) {
+      // (reads past R stay inside the list's slack only for ONE batch: guard the second prefetch)
+      if (base + STEP < R) fetch(base + STEP, idB, wB, bpB);
+      score(base, idA, wA, bpA);
+      if (base + STEP >= R) break;
+      if (base + 2 * STEP < R) fetch(base + 2 * STEP, idA, wA, bpA);
+      score(base + STEP, idB, wB, bpB);
+    }
+  } else {
+    for (int base = 0; base < R; base += STEP) {
+      int id[UNR];
+      float4 w[UNR][NV];
+      float bp[UNR];
+      fetch(base, id, w, bp);
+      score(base, id, w, bp);
     }
   }
   if (TRAIN) {
