@@ -41,13 +41,13 @@ SEED = 20141119
 
 CONFIGS = {
     "B": dict(users_per_gpu=100_000, items=50_000, mean=30.0, K=50, num_neg=5, asym=False, full=False,
-              batch=8192, gpus=1, metric="users/sec CDAE training (K=50, Yelp-scale)",
+              batch=16384, gpus=1, metric="users/sec CDAE training (K=50, Yelp-scale)",
               what="synthetic %dK users x 50K items, K=50, neg-sample=5, %dxB200"),
     "C": dict(users_per_gpu=138_000, items=27_000, mean=145.0, K=200, num_neg=5, asym=True, full=True,
               batch=0, gpus=1, metric="users/sec CDAE training (K=200, MovieLens-20M-scale, full-item decode)",
               what="MovieLens-20M-scale synthetic (%dK x 27K), K=200, full-item decode, %dxB200"),
     "D": dict(users_per_gpu=125_000, items=200_000, mean=30.0, K=100, num_neg=5, asym=False, full=False,
-              batch=8192, gpus=8, metric="users/sec CDAE training (K=100, Yelp-scale 1M x 200K)",
+              batch=16384, gpus=8, metric="users/sec CDAE training (K=100, Yelp-scale 1M x 200K)",
               what="Yelp-scale synthetic %dK x 200K, K=100, neg-sample=5, user-sharded %dxB200"),
     "E": dict(users_per_gpu=62_500, items=100_000, mean=50.0, K=256, num_neg=5, asym=True, full=True,
               batch=0, gpus=8, metric="users/sec CDAE training (K=256, 500K x 100K, full-item decode bf16)",
@@ -609,7 +609,7 @@ def main():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json configuration (default B)")
     ap.add_argument("--extra", default=None, help="comma list of further configurations to add under `configs`")
     ap.add_argument("--no-extra", action="store_true", help="only the primary configuration")
-    ap.add_argument("--batch-users", type=int, default=0, help="config B: users per minibatch per GPU (default 8192)")
+    ap.add_argument("--batch-users", type=int, default=0, help="config B: users per minibatch per GPU (default 16384)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p", "nvls"],
                     help="combine step: auto = NVLS kernel where multicast is available, else the peer-memory kernel")
     ap.add_argument("--cpu-sample", type=int, default=30000,

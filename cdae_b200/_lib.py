@@ -95,6 +95,7 @@ SIGNATURES = {
     "cdae_profile_get": (C.c_int, [C.c_void_p, f64p, i64p]),
     "cdae_probe_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, f64p, f64p]),
     "cdae_debug_combine": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cdae_debug_combine_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "cdae_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "cdae_host_free": (C.c_int, [C.c_void_p]),
     "cdae_synchronize": (C.c_int, [C.c_void_p]),

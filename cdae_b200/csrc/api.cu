@@ -508,7 +508,7 @@ static int combine_and_apply(cdae_handle* h) {
     ma.flags = reinterpret_cast<const uint32_t*>(h->mc_uc);
     ma.params = h->item_params.p;
     ma.acc = h->item_acc.p;
-    ma.grad_next = h->grad.p + nxt;
+    ma.grad_next = getenv("CDAE_B200_DEBUG_NOZERO") ? nullptr : h->grad.p + nxt;   // (debug: timing without the zeroing pass)
     ma.done = h->p2p_done;
     ma.bad_csr_out = &h->stats_d->bad_csr;
     ma.rank = h->rank; ma.world = h->world;
@@ -524,6 +524,7 @@ static int combine_and_apply(cdae_handle* h) {
     ma.cnt_off = (int64_t)(h->m.gcnt - h->m.gW);
     ma.steps_off = (int64_t)(h->m.g_steps - h->m.gW);
     ma.lr = h->m.lr; ma.beta = h->m.beta; ma.lambda = h->m.lambda; ma.adagrad = h->m.adagrad;
+    ma.ts = h->p2p_ts;
     p2p::mc_step_kernel<<<h->sm_count * 2, 512, 0, h->stream>>>(ma);
     KERNEL_OK(h);
     h->p2p_parity ^= 1;
@@ -540,7 +541,7 @@ static int combine_and_apply(cdae_handle* h) {
       fa.flags[r] = h->p2p_flags[r];
     }
     fa.acc = h->item_acc.p;
-    fa.grad_next = h->grad.p + nxt;
+    fa.grad_next = getenv("CDAE_B200_DEBUG_NOZERO") ? nullptr : h->grad.p + nxt;   // (debug: timing without the zeroing pass)
     fa.done = h->p2p_done;
     fa.bad_csr_out = &h->stats_d->bad_csr;
     fa.rank = h->rank; fa.world = h->world;
@@ -558,6 +559,7 @@ static int combine_and_apply(cdae_handle* h) {
     fa.steps_off = (int64_t)(h->m.g_steps - h->m.gW);
     fa.steps_slot = 0;
     fa.lr = h->m.lr; fa.beta = h->m.beta; fa.lambda = h->m.lambda; fa.adagrad = h->m.adagrad;
+    fa.ts = h->p2p_ts;
     p2p::fused_step_kernel<<<h->sm_count * 2, 512, 0, h->stream>>>(fa);   // 2 resident CTAs per SM: more NVLink loads in flight
     KERNEL_OK(h);
     h->p2p_parity ^= 1;
@@ -696,7 +698,7 @@ int cdae_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int64_t* r
   h->ld = row_stride(cfg->num_dim);
   h->I4 = round_up(I, 4);
   h->nnz = row_ptr[U];
-  h->batch_users = cfg->batch_users > 0 ? cfg->batch_users : 8192;
+  h->batch_users = cfg->batch_users > 0 ? cfg->batch_users : 16384;   // default: profiles/r02_h_batch_size_sweep.json + r02_d_* (trajectory)
   h->ch_in = 64;
   h->ch_out = std::max(1, 96 / (1 + cfg->num_neg));
   h->rank = 0; h->world = 1;
@@ -779,6 +781,7 @@ int cdae_destroy(cdae_handle* h) {
     if (h->p2p_flags[r]) cudaIpcCloseMemHandle(h->p2p_flags[r]);
   }
   if (h->p2p_my_flags) cudaFree(h->p2p_my_flags);
+  if (h->p2p_ts) cudaFree(h->p2p_ts);
   mc_release(h);   // NVLS mode: the item-side buffers belong to a VMM block, not to cudaMalloc
   ModelDev& m = h->m;
   float* tabs[] = {m.Wu, m.Uu, m.Wu_ag, m.Uu_ag};
@@ -1390,12 +1393,28 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
 int cdae_debug_combine(cdae_handle* h, int32_t reps) {
   if (!h || reps <= 0) return set_error(CDAE_E_INVALID, "bad argument");
   TRY(begin_call(h));
+  if (!h->p2p_ts) {
+    CU(cudaMalloc(&h->p2p_ts, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(h->p2p_ts, 0, 8 * sizeof(unsigned long long)));
+  }
   for (int r = 0; r < reps; ++r) {
     // 0x2f2f2f2f = 1.59e-10f: every element has a (tiny) gradient, so every parameter is rewritten and published
     CU(cudaMemsetAsync(h->m.gW, 0x2f, sizeof(float) * (size_t)(h->m.gcnt - h->m.gW), h->stream));
     TRY(combine_and_apply(h));
   }
   return end_call(h, nullptr);
+}
+
+// %globaltimer (ns) of the LAST fused combine kernel: [0] entry, [1] every peer's gradients complete, [2] block 0
+// finished its slice (loads, optimiser step, stores, zeroing), [3] all blocks done, [4] every peer's stores are in
+int cdae_debug_combine_times(cdae_handle* h, uint64_t* out5) {
+  if (!h || !out5) return set_error(CDAE_E_INVALID, "NULL argument");
+  if (!h->p2p_ts) return set_error(CDAE_E_STATE, "cdae_debug_combine has not run");
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long t[8];
+  CU(cudaMemcpy(t, h->p2p_ts, sizeof(t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 5; ++i) out5[i] = t[i];
+  return 0;
 }
 
 int cdae_host_alloc(void** ptr, int64_t bytes) {

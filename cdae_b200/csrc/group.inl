@@ -55,7 +55,7 @@ int cdae_group_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int6
     cdae_config_t c = *cfg;
     c.device = devices ? devices[r] : r;
     // the minibatch of the config is the GLOBAL one; by default every GPU keeps the single-GPU share
-    if (c.batch_users <= 0 && !c.full_decode) c.batch_users = 8192 * n;
+    if (c.batch_users <= 0 && !c.full_decode) c.batch_users = 16384 * n;
     cdae_handle* h = nullptr;
     const int rc = cdae_create(&c, U, I, row_ptr, col, &h);
     if (rc != 0) { cdae_group_destroy(g); return rc; }

@@ -51,6 +51,7 @@ struct cdae_handle {
   uint32_t* p2p_flags[8] = {nullptr};
   uint32_t* p2p_my_flags = nullptr;
   unsigned int* p2p_done = nullptr;
+  unsigned long long* p2p_ts = nullptr;   // phase timestamps of the fused combine kernel (cdae_debug_combine only)
   int p2p_parity = 0;              // which gradient buffer the current minibatch accumulates into
   // NVLS mode (mc_nvls.inl): the item side lives in a VMM block bound to a multicast object
   bool mc_creator = false, mc_attached = false, mc_active = false;

@@ -163,14 +163,18 @@ struct FusedArgs {
   int steps_slot;
   float lr, beta, lambda;
   int adagrad;
+  unsigned long long* ts;          // nullable: %globaltimer at the phase boundaries of block 0 / the last block (cdae_debug_combine)
 };
+#define P2P_STAMP(slot) do { if (a.ts && threadIdx.x == 0) a.ts[slot] = global_ns(); } while (0)
 
 __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
   if (blockIdx.x == 0) {
+    P2P_STAMP(0);
     __threadfence_system();
     announce(a.flags, a.rank, a.world, a.epoch);
   }
   wait_all(a.flags, a.rank, a.world, a.epoch, a.bad_csr_out);
+  if (blockIdx.x == 0) P2P_STAMP(1);
 
   // scalars every element may need: user steps of the minibatch (n * lambda * b) and the bad-CSR flag.  ONE
   // thread per peer and block fetches them (every thread doing so made 10^5 - 10^6 requests for the same two
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
           s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
         }
     }
-    if (first_pass) {
+    if (first_pass && a.grad_next) {
       // zero the gradient buffer the PREVIOUS minibatch consumed while the peer loads above are in flight
       first_pass = false;
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride)
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
         if (p < a.world) st_peer_v4(a.params[p] + i * 4, wn);
     }
   }
+  if (blockIdx.x == 0) P2P_STAMP(2);
 
   // last block out: "my stores are out" -> wait until everybody's are in.  One system-scope fence per block,
   // after the block barrier, orders every thread's stores (fence cumulativity — the grid.sync() pattern)
@@ -267,10 +272,12 @@ __global__ void __launch_bounds__(512) fused_step_kernel(FusedArgs a) {
   }
   __syncthreads();
   if (last) {
+    P2P_STAMP(3);
     if (threadIdx.x == 0) *a.done = 0u;
     __threadfence_system();
     announce(a.flags, a.rank, a.world, a.epoch + 1);
     wait_all(a.flags, a.rank, a.world, a.epoch + 1, a.bad_csr_out);
+    P2P_STAMP(4);
   }
 }
 
@@ -318,6 +325,7 @@ struct McArgs {
   int64_t cnt_off, steps_off;
   float lr, beta, lambda;
   int adagrad;
+  unsigned long long* ts;          // nullable (cdae_debug_combine)
 };
 
 __device__ __forceinline__ void mc_wait(const uint32_t* counter, uint32_t target, int* timeout_flag) {
@@ -336,10 +344,12 @@ __device__ __forceinline__ void mc_wait(const uint32_t* counter, uint32_t target
 __global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
   // stream order: every kernel that added to this rank's gradients has finished
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    P2P_STAMP(0);
     __threadfence_system();
     mc_red_add_release(a.mc_flags + 0, 1u);
   }
   mc_wait(a.flags + 0, a.target, a.bad_csr_out);
+  if (blockIdx.x == 0) P2P_STAMP(1);
   __shared__ float sc_s[2];
   if (threadIdx.x < 2) sc_s[threadIdx.x] = mc_ld_sum_f32(a.mc_grad + a.steps_off + (threadIdx.x == 0 ? 0 : 2));
   __syncthreads();
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
       if (!on[u]) continue;
       s[u] = mc_ld_sum_v4(a.mc_grad + i * 4);
     }
-    if (first_pass) {
+    if (first_pass && a.grad_next) {
       // zero the gradient buffer the PREVIOUS minibatch consumed while the switch reductions are in flight
       first_pass = false;
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride)
@@ -399,6 +409,7 @@ __global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
       mc_st_v4(a.mc_params + i * 4, make_float4(w[0], w[1], w[2], w[3]));
     }
   }
+  if (blockIdx.x == 0) P2P_STAMP(2);
   __syncthreads();
   __shared__ bool last;
   if (threadIdx.x == 0) {
@@ -407,12 +418,14 @@ __global__ void __launch_bounds__(512) mc_step_kernel(McArgs a) {
   }
   __syncthreads();
   if (last) {
+    P2P_STAMP(3);
     if (threadIdx.x == 0) {
       *a.done = 0u;
       __threadfence_system();
       mc_red_add_release(a.mc_flags + 1, 1u);
     }
     mc_wait(a.flags + 1, a.target, a.bad_csr_out);
+    P2P_STAMP(4);
   }
 }
 

@@ -375,7 +375,7 @@ class CDAE:
 class CDAEGroup(CDAE):
     """`class CDAE` on several GPUs of ONE process (cdae_group_*, csrc/group.inl): one engine handle per
     device, users sharded like a process group, one worker thread per GPU inside every call.
-    config.batch_users is the GLOBAL minibatch (0 -> 8192 per GPU)."""
+    config.batch_users is the GLOBAL minibatch (0 -> 16384 per GPU)."""
 
     def __init__(self, config=None, devices=(0, 1)):
         super().__init__(config)

@@ -80,7 +80,7 @@ typedef struct cdae_config {
   int32_t linear_function;
   int32_t tanh_act;
   /* ---- device options (no reference counterpart) ---- */
-  int32_t batch_users;        /* users per frozen minibatch; 0 -> 8192.  1 reproduces the
+  int32_t batch_users;        /* users per frozen minibatch; 0 -> 16384.  1 reproduces the
                                  reference's per-user online step. */
   int32_t device;             /* CUDA device ordinal */
   int32_t full_decode;        /* 1: full-item decode — every user's output set is ALL items (target 1
@@ -265,7 +265,7 @@ int cdae_dist_mc_bind(cdae_handle* h);
  * like a process group of `n` ranks (same user sharding, same fused combine step over peer memory —
  * NVLS where available — with NCCL for the read-backs), so libcf::CDAE can use the whole box:
  * cdae_b200/host/model/recsys/cdae.hpp switches to it with CDAE_B200_GPUS=n.  cfg->batch_users is the
- * GLOBAL minibatch (0 -> 8192 per GPU); devices NULL -> 0..n-1.  Every cdae_group_X is the collective
+ * GLOBAL minibatch (0 -> 16384 per GPU); devices NULL -> 0..n-1.  Every cdae_group_X is the collective
  * form of cdae_X; cdae_group_topn_lookup (thread-safe) and cdae_group_encode route each user to the
  * GPU that trains it.  cdae_group_handle exposes one GPU's handle, e.g. for item-side (replicated) reads. */
 typedef struct cdae_group cdae_group;
@@ -319,6 +319,10 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
  * (collective in a process group; with cdae_profile on, the allreduce / apply classes hold its pure
  * device time — no user work in front of it, hence no rank skew).  Parameters drift by ~1e-10 per call. */
 int cdae_debug_combine(cdae_handle* h, int32_t reps);
+/* %globaltimer (ns) at the phase boundaries of the last fused combine kernel cdae_debug_combine launched:
+ * [0] entry, [1] all peers' gradients complete, [2] block 0 done with its slice, [3] all blocks done,
+ * [4] all peers' stores are in. */
+int cdae_debug_combine_times(cdae_handle* h, uint64_t* out5);
 
 /* pinned host memory for buffers that cross the boundary every step */
 int cdae_host_alloc(void** ptr, int64_t bytes);

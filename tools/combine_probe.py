@@ -17,7 +17,13 @@ def main():
         return box
     out = {}
     for name, I, K in (("B", 50_000, 50), ("D", 200_000, 100), ("E", 100_000, 256)):
-        for mode in ("nccl", "p2p", "nvls"):
+        for mode in ("nccl", "p2p", "nvls", "p2p-nozero", "nvls-nozero"):
+            os.environ.pop("CDAE_B200_DEBUG_NOZERO", None)
+            if mode.endswith("-nozero"):
+                os.environ["CDAE_B200_DEBUG_NOZERO"] = "1"
+                mode_real = mode[:-7]
+            else:
+                mode_real = mode
             U = 64 * world
             rp = np.arange(U + 1, dtype=np.int64) * 2
             col = np.tile(np.array([0, 1], np.int32), U)
@@ -25,9 +31,9 @@ def main():
             uid = [CDAE.dist_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             m.dist_init(rank, world, uid[0])
-            if mode == "p2p":
+            if mode_real == "p2p":
                 m.dist_p2p_init(gather)
-            elif mode == "nvls" and not m.dist_mc_init(rank, world, gather):
+            elif mode_real == "nvls" and not m.dist_mc_init(rank, world, gather):
                 m.close(); continue
             m.init_params(1)
             _lib.check(m._L.cdae_debug_combine(m._h, 5))
@@ -40,6 +46,14 @@ def main():
             t = torch.tensor([us], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             out["%s %s" % (name, mode)] = round(t.item(), 1)
+            if mode_real != "nccl":
+                import ctypes as C
+                ts = (C.c_uint64 * 5)()
+                _lib.check(m._L.cdae_debug_combine_times(m._h, ts))
+                ph = [round((ts[i + 1] - ts[i]) / 1e3, 1) for i in range(4)]
+                allp = gather(ph)
+                if rank == 0:
+                    out["%s %s phases_us [wait peers, slice work, other blocks, closing barrier] per rank" % (name, mode)] = allp
             m.close()
     if rank == 0:
         print(json.dumps({"world": world, "combine_plus_apply_us_max_over_ranks": out}))
