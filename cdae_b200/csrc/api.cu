@@ -643,7 +643,7 @@ static int end_call(cdae_handle* h, cdae_epoch_stats_t* stats) {
   if (h->stats_h->bad_csr) h->csr_bad = true;
   if (h->stats_h->bad_csr)
     return set_error(CDAE_E_INVALID, "the CSR passed to cdae_train_epoch_csr has an item id outside [0,%lld) or a row that is "
-                     "not strictly ascending; no parameter was updated", (long long)h->I);
+                     "not strictly ascending; the offending minibatch and all later ones were not applied", (long long)h->I);
   if (h->stats_h->bad_loss)
     return set_error(CDAE_E_NUMERIC, "LOGISTIC loss received a score outside (0,1) "
                      "(the reference CHECK-aborts here, loss.hpp:96; use CROSS_ENTROPY)");
@@ -800,6 +800,8 @@ int cdae_destroy(cdae_handle* h) {
   h->fd_zb.release(); h->fd_wb.release(); h->fd_g.release(); h->fd_bits.release(); h->fd_bias.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);
+  for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -957,19 +959,26 @@ static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_e
     // trained user checks it on the device (item ids in range — out-of-range ids are clamped in the
     // device copy so no kernel can index outside a table — and rows strictly ascending); a violation
     // raises stats->bad_csr and the shared flag g_steps[2], which make hidden_backward / uu_update /
-    // apply skip their updates, and the call returns CDAE_E_INVALID with the parameters untouched.
+    // apply skip their updates from that minibatch on; the call returns CDAE_E_INVALID.
+    // The upload runs on a second stream, one piece per minibatch (cdae_train_epoch_csr), and each
+    // minibatch only waits for — and checks — its own rows: PCIe transfer of minibatch k + 1 overlaps the
+    // kernels of minibatch k.
     CU(cudaMemsetAsync(h->m.g_steps + 2, 0, sizeof(float), h->stream));
-    const int64_t n = (int64_t)h->plan_n_uids;
-    if (n > 0) {
-      validate_rows_kernel<<<cdiv(n * 32, 256), 256, 0, h->stream>>>(h->plan_uids.p, n, h->row_ptr_d.p, h->col_d.p,
-                                                                 h->I, h->stats_d, h->m.g_steps + 2);
-      KERNEL_OK(h);
-    }
-    h->csr_unchecked = false;
+    CU(cudaStreamWaitEvent(h->stream, h->copy_ev[0], 0));     // row_ptr
   }
+  const bool staged = h->csr_unchecked;
+  h->csr_unchecked = false;
   TRY(ensure_scratch(h, h->plan_max_users, h->plan_max_slots));
   const int cnum = h->cfg.num_corruptions;
+  size_t mb_index = 0;
   for (const MiniBatch& p : h->plan) {
+    ++mb_index;
+    if (staged && p.n_users > 0) {
+      CU(cudaStreamWaitEvent(h->stream, h->copy_ev[mb_index], 0));
+      validate_rows_kernel<<<cdiv(p.n_users * 32, 256), 256, 0, h->stream>>>(h->plan_uids.p + p.user0, p.n_users, h->row_ptr_d.p,
+                                                                          h->col_d.p, h->I, h->stats_d, h->m.g_steps + 2);
+      KERNEL_OK(h);
+    }
     for (int c = 0; c < cnum; ++c) {
       BatchDev bt = make_batch(h, h->plan_in.p + p.in0, p.n_in, h->plan_out.p + p.out0, p.n_out,
                                h->plan_uids.p + p.user0, p.n_users);
@@ -1021,23 +1030,45 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
     h->plan_valid = false;
     TRY(ensure(h, h->col_d, (size_t)std::max<int64_t>(nnz, 1)));
   }
+  // Upload on a second stream, in minibatch order: [row_ptr] then the col range of every minibatch this rank
+  // trains, an event after each piece.  The compute stream waits per minibatch (train_epoch_impl), so the
+  // transfer of minibatch k + 1 rides under the kernels of minibatch k.  (The previous call ended with a
+  // synchronise of the compute stream, so nothing still reads the old device copy.)
+  if (!h->plan_valid) TRY(build_plan(h));
+  if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  while (h->copy_ev.size() < h->plan.size() + 1) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->copy_ev.push_back(e);
+  }
   if (h->world == 1) {
-    CU(cudaMemcpyAsync(h->row_ptr_d.p, row_ptr, sizeof(int64_t) * (h->U + 1), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->col_d.p, col, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
-    h->h2d += sizeof(int64_t) * (h->U + 1) + sizeof(int32_t) * nnz;
+    CU(cudaMemcpyAsync(h->row_ptr_d.p, row_ptr, sizeof(int64_t) * (h->U + 1), cudaMemcpyHostToDevice, h->copy_stream));
+    h->h2d += sizeof(int64_t) * (h->U + 1);
   } else {
-    if (!h->plan_valid) TRY(build_plan(h));
     for (const MiniBatch& p : h->plan) {
       if (p.n_users == 0) continue;
-      const int64_t s0 = row_ptr[p.uid0], s1 = row_ptr[p.uid0 + p.n_users];
-      CU(cudaMemcpyAsync(h->row_ptr_d.p + p.uid0, row_ptr + p.uid0, sizeof(int64_t) * (p.n_users + 1), cudaMemcpyHostToDevice, h->stream));
-      if (s1 > s0) CU(cudaMemcpyAsync(h->col_d.p + s0, col + s0, sizeof(int32_t) * (s1 - s0), cudaMemcpyHostToDevice, h->stream));
-      h->h2d += sizeof(int64_t) * (p.n_users + 1) + sizeof(int32_t) * (s1 - s0);
+      CU(cudaMemcpyAsync(h->row_ptr_d.p + p.uid0, row_ptr + p.uid0, sizeof(int64_t) * (p.n_users + 1), cudaMemcpyHostToDevice, h->copy_stream));
+      h->h2d += sizeof(int64_t) * (p.n_users + 1);
+    }
+  }
+  CU(cudaEventRecord(h->copy_ev[0], h->copy_stream));
+  {
+    size_t k = 0;
+    for (const MiniBatch& p : h->plan) {
+      ++k;
+      if (p.n_users > 0) {
+        const int64_t s0 = row_ptr[p.uid0], s1 = row_ptr[p.uid0 + p.n_users];
+        if (s1 > s0) CU(cudaMemcpyAsync(h->col_d.p + s0, col + s0, sizeof(int32_t) * (s1 - s0), cudaMemcpyHostToDevice, h->copy_stream));
+        h->h2d += sizeof(int32_t) * (s1 - s0);
+      }
+      CU(cudaEventRecord(h->copy_ev[k], h->copy_stream));
     }
   }
   h->csr_unchecked = true;
   h->csr_bad = false;
-  return train_epoch_impl(h, seed, epoch, stats);
+  const int rc = train_epoch_impl(h, seed, epoch, stats);
+  if (rc != 0) cudaStreamSynchronize(h->copy_stream);   // the caller's buffers must not be read after an error return
+  return rc;
 }
 
 // Upload the work lists of an explicit user list into the tmp_* buffers.

@@ -65,6 +65,8 @@ struct cdae_handle {
   size_t dev_bytes = 0;
 
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // cdae_train_epoch_csr: host -> device pieces, one event per minibatch
+  std::vector<cudaEvent_t> copy_ev;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cdae::ModelDev m;
   // item side: parameters, AdaGrad state and minibatch gradients as flat buffers of ONE layout

@@ -142,11 +142,13 @@ int cdae_train_epoch(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_st
 /* Same, with the training CSR taken from HOST memory on every call, the way
  * train_one_iteration(const Data&) receives its data each epoch.  Shapes must match
  * cdae_create (same U; nnz may differ).  H2D copy and the D2H read of stats are inside
- * the call.  row_ptr is checked on the host when it changed; col is checked ON THE DEVICE after the
- * upload (ids in [0, I), rows strictly ascending; in a process group each rank checks the rows it
- * trains): a violation returns CDAE_E_INVALID with no parameter updated (out-of-range ids are clamped
- * in the device copy, so no kernel indexes outside a table), and training calls are refused until a
- * valid CSR is passed. */
+ * the call.  The upload runs on a second stream, one piece per minibatch, under the kernels of the
+ * previous minibatch.  row_ptr is checked on the host when it changed; col is checked ON THE DEVICE as
+ * each minibatch's rows arrive (ids in [0, I), rows strictly ascending; in a process group each rank
+ * checks the rows it trains): a violation returns CDAE_E_INVALID — the offending minibatch and every
+ * later one leave the parameters untouched, earlier minibatches of the call have been trained
+ * (out-of-range ids are clamped in the device copy, so no kernel indexes outside a table) — and
+ * training calls are refused until a valid CSR is passed. */
 int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* col_idx,
                          uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats);
 

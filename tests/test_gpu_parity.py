@@ -334,10 +334,10 @@ def test_q1_scaled_losses_are_finite(orc):
         assert ids[u].tolist() == o.recommend(u, 10)[0].tolist()
 
 
-def test_train_epoch_csr_rejects_a_bad_csr_without_touching_parameters(orc):
-    """the host-CSR call must not index tables with unchecked ids.  The column array is
-    checked on the device; a violation is an error, the parameters stay as they were, and training is
-    refused until a valid CSR arrives."""
+def test_train_epoch_csr_rejects_a_bad_csr(orc):
+    """the host-CSR call must not index tables with unchecked ids.  The column array is checked on
+    the device, minibatch by minibatch as its rows arrive; a violation is an error, the offending minibatch and
+    all later ones leave the parameters as they were, and training is refused until a valid CSR arrives."""
     from cdae_b200 import CdaeError
     cfg = orc.default_config(loss="CE", beta=1.0)
     data = cases.small_dataset(U=150, I=300, mean=10.0, seed=6)
@@ -358,11 +358,19 @@ def test_train_epoch_csr_rejects_a_bad_csr_without_touching_parameters(orc):
         with pytest.raises(CdaeError):
             m.train_one_iteration(seed=3, epoch=0, csr=(rp, bad))
         after = m.get_params()
-        for k in before:
-            assert np.array_equal(before[k], after[k]), (kind, k)
+        # the upload is pipelined per minibatch (64 users here): the minibatch before the offending one (users
+        # 0..63) has been trained, the offending one (user 70) and every later one have not touched anything
+        assert np.array_equal(before["Wu"][64:], after["Wu"][64:]), kind
+        assert not np.array_equal(before["Wu"][:64], after["Wu"][:64]), kind
+        o = orc.Oracle(cfg, U, I, rp, col)
+        o.set_params(p)
+        o.train_epoch(3, 0, batch_users=64, u0=0, u1=64)
+        for k in ("W", "b", "b_prime", "Wu"):
+            np.testing.assert_allclose(after[k], o.param(k).reshape(after[k].shape), rtol=P_RTOL, atol=P_ATOL, err_msg=kind + " " + k)
         with pytest.raises(CdaeError):
             m.train_one_iteration(seed=3, epoch=0)                       # resident CSR is known bad
         # a valid CSR heals the handle and trains exactly like a fresh one
+        m.set_params(p)
         m.train_one_iteration(seed=3, epoch=0, csr=(rp, col))
         m2 = gpu_model(cfg, U, I, rp, col, p, batch_users=64)
         m2.train_one_iteration(seed=3, epoch=0)
