@@ -314,7 +314,10 @@ def measure(name, ctx, args, primary):
                 box = [None] * world
                 dist.all_gather_object(box, b)
                 return box
-            if args.allreduce in ("auto", "nvls") and os.environ.get("CDAE_B200_NVLS", "1") != "0" and m.dist_mc_init(rank, world, gather):
+            # NVLS wins where the peer-memory kernel is NVLink-bound (8 GPUs: 71 vs 85 us per 13.6 MB step); on 2-4 GPUs the
+            # peer kernel is faster (52 vs 73 us, 67 vs 69 us) — profiles/r02_c_combine_probe_*.json
+            want_nvls = args.allreduce == "nvls" or (args.allreduce == "auto" and world >= 8)
+            if want_nvls and os.environ.get("CDAE_B200_NVLS", "1") != "0" and m.dist_mc_init(rank, world, gather):
                 allreduce = ctx.nvls_label
             else:
                 m.dist_p2p_init(gather)

@@ -70,7 +70,9 @@ int cdae_group_create(const cdae_config_t* cfg, int64_t U, int64_t I, const int6
     static const bool want_p2p = !(getenv("CDAE_B200_P2P") && atoi(getenv("CDAE_B200_P2P")) == 0);
     static const bool want_mc = !(getenv("CDAE_B200_NVLS") && atoi(getenv("CDAE_B200_NVLS")) == 0);
     bool mc_ok = false;
-    if (rc == 0 && want_p2p && want_mc) {
+    // (NVLS pays off where the peer-memory kernel is NVLink-bound: 8 GPUs; on 2-4 GPUs the peer kernel is faster)
+    const bool force_mc = getenv("CDAE_B200_NVLS") && atoi(getenv("CDAE_B200_NVLS")) == 1;
+    if (rc == 0 && want_p2p && want_mc && (n >= 8 || force_mc)) {
       int32_t fd = -1;
       if (cdae_dist_mc_create(g->h[0], &fd) == 0) {
         if (fd >= 0) close(fd);

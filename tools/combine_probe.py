@@ -16,8 +16,11 @@ def main():
         dist.all_gather_object(box, b)
         return box
     out = {}
-    for name, I, K in (("B", 50_000, 50), ("D", 200_000, 100), ("E", 100_000, 256)):
-        for mode in ("nccl", "p2p", "nvls", "p2p-nozero", "nvls-nozero"):
+    shapes = (("B", 50_000, 50), ("D", 200_000, 100), ("E", 100_000, 256))
+    if os.environ.get("PROBE_SHAPES"):
+        shapes = tuple(x for x in shapes if x[0] in os.environ["PROBE_SHAPES"].split(","))
+    for name, I, K in shapes:
+        for mode in ("nccl", "p2p", "nvls"):
             os.environ.pop("CDAE_B200_DEBUG_NOZERO", None)
             if mode.endswith("-nozero"):
                 os.environ["CDAE_B200_DEBUG_NOZERO"] = "1"
