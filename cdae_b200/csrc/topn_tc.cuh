@@ -43,7 +43,12 @@ constexpr int CAND_MAX = 96;  // largest per-user candidate buffer
 #ifndef TC_KB4_EPI
 #define TC_KB4_EPI 1   // A/B switch (CDAE_NVCC_FLAGS=-DTC_KB4_EPI=2): paired epilogue warps for 4 k-blocks too
 #endif
-__host__ __device__ constexpr int epi_warps(int kb) { return kb <= 3 ? 2 : (kb == 4 ? TC_KB4_EPI : 1); }
+#ifndef TC_KB1_EPI
+#define TC_KB1_EPI 2   // A/B switch (-DTC_KB1_EPI=4): at K <= 62 a tile is 4 UMMAs followed by 32 K score reads, so the
+#endif                 // epilogue is the critical path — but FOUR warps per TMEM lane quadrant measured 3.95 ms against
+                       // 2.27 ms with two at config B (24-slot candidate buffers compact far more often, 96 registers
+                       // with spills, a 16-warp barrier per tile); profiles/r02_j_topn_epilogue_ab.json
+__host__ __device__ constexpr int epi_warps(int kb) { return kb == 1 ? TC_KB1_EPI : kb <= 3 ? 2 : (kb == 4 ? TC_KB4_EPI : 1); }
 // candidate slots per user (all buffers together): what is left of the 227 KB after A and B
 __host__ __device__ constexpr int cand_slots(int kb) {
   return kb == 1 ? 96 : kb == 2 ? 80 : kb == 3 ? 64 : kb == 4 ? (TC_KB4_EPI == 2 ? 54 : 48) : 36;
@@ -51,12 +56,13 @@ __host__ __device__ constexpr int cand_slots(int kb) {
 __host__ __device__ constexpr int buf_slots(int kb) { return cand_slots(kb) / epi_warps(kb); }
 // a compaction keeps between keep_lo and keep_hi entries of a buffer
 __host__ __device__ constexpr int keep_hi(int kb) { return buf_slots(kb) / 2; }
-__host__ __device__ constexpr int keep_lo(int kb) { return keep_hi(kb) - 8 > 12 ? keep_hi(kb) - 8 : 12; }
+__host__ __device__ constexpr int keep_lo(int kb) { return keep_hi(kb) - 8 > 12 ? keep_hi(kb) - 8 : (keep_hi(kb) > 12 ? 12 : 10); }
 __host__ __device__ constexpr int n_threads(int kb) { return 128 + 128 * epi_warps(kb); }
 constexpr int BM_BYTES = 2 * 8 * TILE_U * 4;  // two rated bitmaps [8 words][128 rows]
 __host__ __device__ constexpr size_t smem_bytes(int kb) {
   return 1024 /*alignment slack*/ + (size_t)kb * A_BLK_BYTES + (size_t)NSTAGE * B_BLK_BYTES +
-         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + 2 * TILE_U * 8 /*merge*/ + 512 /*exchange, barriers*/;
+         (size_t)cand_slots(kb) * TILE_U * 8 + BM_BYTES + (size_t)(epi_warps(kb) < 2 ? 2 : epi_warps(kb)) * TILE_U * 8 /*merge*/ +
+         (size_t)(epi_warps(kb) < 2 ? 2 : epi_warps(kb)) * 4 * 32 /*hit exchange*/ + 256 /*barriers*/;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -476,11 +482,12 @@ __global__ void __launch_bounds__(n_threads(KB), 1) topn_tc_kernel(const __grid_
   float* cs = reinterpret_cast<float*>(sB + NSTAGE * B_BLK_BYTES);  // [EPI][C2][128]
   int* ci = reinterpret_cast<int*>(cs + C * TILE_U);               // [EPI][C2][128]
   uint32_t* bm = reinterpret_cast<uint32_t*>(ci + C * TILE_U);     // [2][8][128]
-  int* mcnt = reinterpret_cast<int*>(bm + 2 * 8 * TILE_U);          // [2][128] final counts per buffer
-  float* mthr = reinterpret_cast<float*>(mcnt + 2 * TILE_U);        // [2][128] final thresholds
-  volatile int* creq = reinterpret_cast<volatile int*>(mthr + 2 * TILE_U);  // [2] tile that asked for a compaction
-  float* xch_all = mthr + 2 * TILE_U + 4;                            // [8 epilogue warps][8] hit exchange (16-byte aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_all + 8 * 8);
+  constexpr int EPW = EPI < 2 ? 2 : EPI;                            // rows of the merge arrays
+  int* mcnt = reinterpret_cast<int*>(bm + 2 * 8 * TILE_U);          // [EPW][128] final counts per buffer
+  float* mthr = reinterpret_cast<float*>(mcnt + EPW * TILE_U);      // [EPW][128] final thresholds
+  volatile int* creq = reinterpret_cast<volatile int*>(mthr + EPW * TILE_U);  // [2] tile that asked for a compaction
+  float* xch_all = mthr + EPW * TILE_U + 4;                          // [4 * EPW epilogue warps][8] hit exchange (16-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_all + 4 * EPW * 8);
   uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA -> TMA
   uint64_t* a_full = bars + 2 * NSTAGE;  // A tile landed
