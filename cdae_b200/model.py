@@ -324,7 +324,10 @@ class CDAE:
             fd = fds[0]
         rc = self._L.cdae_dist_mc_attach(self._h, fd)
         if not all(all_gather(rc == 0)):
-            raise CdaeError(rc, "cdae_dist_mc_attach failed on some rank: " + self._L.cdae_last_error().decode("utf-8", "replace"))
+            # nothing on the training path has changed yet: every rank falls back together
+            if rank != 0:
+                os.close(fd)
+            return False
         rc = self._L.cdae_dist_mc_bind(self._h)              # (the all_gather above was the barrier "everyone attached")
         if not all(all_gather(rc == 0)):
             raise CdaeError(rc, "cdae_dist_mc_bind failed on some rank: " + self._L.cdae_last_error().decode("utf-8", "replace"))
