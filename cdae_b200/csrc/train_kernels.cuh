@@ -443,6 +443,9 @@ __global__ void __launch_bounds__(256) activate_kernel(ModelDev m, BatchDev bt, 
 #ifndef DECODE_PIPE
 #define DECODE_PIPE 1      // 1: loads of the next row batch are issued before the current batch is scored (see decode_kernel)
 #endif
+#ifndef DECODE_STAGE
+#define DECODE_STAGE 0     // > 0: rows staged in shared memory by cp.async, that many batches ahead (A/B; see decode_kernel)
+#endif
 #ifndef DECODE_UNR
 #define DECODE_UNR 0       // row batches in flight per warp; 0 = by geometry (pipelined: 2 for NV = 1, else 1 — two batches live in registers)
 #endif
@@ -487,6 +490,14 @@ __device__ __forceinline__ void red_add_f32_if(float* addr, float v, int on) {
                : "memory");
 }
 
+// cp.async (LDGSTS): 16 bytes global -> shared without passing through registers; per-thread groups
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // LT >= 0 fixes the loss at compile time (CROSS_ENTROPY and SQUARE, the two that are meaningful for
 // CDAE); LT = -1 reads m.loss at run time.
 //
@@ -507,6 +518,11 @@ __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS > 0 ? DECODE_MIN_BLOCKS
   using RM = RowMap<G, NV>;
   constexpr int NG = RM::NG, UNR = DECODE_UNR > 0 ? DECODE_UNR : (DECODE_PIPE ? (NV == 1 ? 2 : 1) : (NV == 1 ? 4 : NV <= 3 ? 2 : 1)), LD = 4 * G * NV;
   constexpr bool PIPE = DECODE_PIPE && NV <= 3;   // NV = 4: two batches of 4 float4 per lane do not fit the register cap
+  // DECODE_STAGE > 0 (A/B, profiles/r02_l_*): rows travel global -> shared by cp.async, DECODE_STAGE batches ahead,
+  // every lane copying exactly the 16-byte pieces it will read back itself (no cross-lane hand-off, so a per-thread
+  // cp.async.wait_group is the only synchronisation); nothing is held in registers while in flight.
+  constexpr int NST = (DECODE_STAGE > 0 && NV <= 2 && TRAIN) ? DECODE_STAGE : 0;
+  __shared__ __align__(16) float4 stage_s[NST > 0 ? 8 : 1][NST > 0 ? NST : 1][NST > 0 ? UNR * NV : 1][NST > 0 ? 32 : 1];
   constexpr int LIST = DECODE_MAX_ROWS + 1 + NG * UNR;   // (num_neg = 96: 97 rows) + one batch of slack
   __shared__ int32_t rows_s[8][LIST];    // the chunk's outputs: positives, then negatives
   __shared__ float lam_s[8][LIST];       // lambda of each output's row term (0 for a merged positive)
@@ -612,7 +628,41 @@ __global__ void __launch_bounds__(256, DECODE_MIN_BLOCKS > 0 ? DECODE_MIN_BLOCKS
       red_add_f32_if(m.gbp + id[t], ok * fmaf(lambda, bp[t], g), first);
     }
   };
-  if constexpr (PIPE) {
+  if constexpr (NST > 0) {
+    float4 (*st)[UNR * NV][32] = stage_s[threadIdx.x >> 5];
+    auto issue = [&](int base, int slot) {
+#pragma unroll
+      for (int t = 0; t < UNR; ++t) {
+        const int idr = mine[base + t * NG + grp];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cp_async16(&st[slot][t * NV + v][lane], Wl + (int64_t)idr * LD + v * G * 4);
+      }
+    };
+    const int n_b = (R + STEP - 1) / STEP;
+#pragma unroll
+    for (int p = 0; p < NST - 1; ++p) {
+      if (p < n_b) issue(p * STEP, p);
+      cp_async_commit();
+    }
+    for (int b = 0; b < n_b; ++b) {
+      if (b + NST - 1 < n_b) issue((b + NST - 1) * STEP, (b + NST - 1) % NST);
+      cp_async_commit();
+      int id[UNR];
+      float bp[UNR];
+#pragma unroll
+      for (int t = 0; t < UNR; ++t) {
+        id[t] = mine[b * STEP + t * NG + grp];
+        bp[t] = __ldg(m.bp + id[t]);
+      }
+      cp_async_wait<NST - 1>();              // batch b has landed (this thread's own copies)
+      float4 w[UNR][NV];
+#pragma unroll
+      for (int t = 0; t < UNR; ++t)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) w[t][v] = st[b % NST][t * NV + v][lane];
+      score(b * STEP, id, w, bp);
+    }
+  } else if constexpr (PIPE) {
     int idA[UNR], idB[UNR];
     float4 wA[UNR][NV], wB[UNR][NV];
     float bpA[UNR], bpB[UNR];
