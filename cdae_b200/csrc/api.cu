@@ -951,7 +951,11 @@ int cdae_get_param_rows(cdae_handle* h, int which, const int64_t* rows, int64_t 
   return 0;
 }
 
-static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats) {
+// rp_host / col_host != nullptr: cdae_train_epoch_csr — the pieces of the caller's CSR are put on the copy
+// stream minibatch by minibatch, each right before that minibatch's kernels are queued, so the GPU starts on
+// minibatch 0 while the host is still issuing the later pieces.
+static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_epoch_stats_t* stats,
+                            const int64_t* rp_host = nullptr, const int32_t* col_host = nullptr) {
   h->topn_k = 0;  // stored recommendation lists are stale
   if (!h->plan_valid) TRY(build_plan(h));
   if (h->csr_unchecked) {
@@ -964,7 +968,6 @@ static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_e
     // minibatch only waits for — and checks — its own rows: PCIe transfer of minibatch k + 1 overlaps the
     // kernels of minibatch k.
     CU(cudaMemsetAsync(h->m.g_steps + 2, 0, sizeof(float), h->stream));
-    CU(cudaStreamWaitEvent(h->stream, h->copy_ev[0], 0));     // row_ptr
   }
   const bool staged = h->csr_unchecked;
   h->csr_unchecked = false;
@@ -974,6 +977,13 @@ static int train_epoch_impl(cdae_handle* h, uint64_t seed, int64_t epoch, cdae_e
   for (const MiniBatch& p : h->plan) {
     ++mb_index;
     if (staged && p.n_users > 0) {
+      {
+        const int64_t s0 = rp_host[p.uid0], s1 = rp_host[p.uid0 + p.n_users];
+        CU(cudaMemcpyAsync(h->row_ptr_d.p + p.uid0, rp_host + p.uid0, sizeof(int64_t) * (p.n_users + 1), cudaMemcpyHostToDevice, h->copy_stream));
+        if (s1 > s0) CU(cudaMemcpyAsync(h->col_d.p + s0, col_host + s0, sizeof(int32_t) * (s1 - s0), cudaMemcpyHostToDevice, h->copy_stream));
+        h->h2d += sizeof(int64_t) * (p.n_users + 1) + sizeof(int32_t) * (s1 - s0);
+        CU(cudaEventRecord(h->copy_ev[mb_index], h->copy_stream));
+      }
       CU(cudaStreamWaitEvent(h->stream, h->copy_ev[mb_index], 0));
       validate_rows_kernel<<<cdiv(p.n_users * 32, 256), 256, 0, h->stream>>>(h->plan_uids.p + p.user0, p.n_users, h->row_ptr_d.p,
                                                                           h->col_d.p, h->I, h->stats_d, h->m.g_steps + 2);
@@ -1030,10 +1040,10 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
     h->plan_valid = false;
     TRY(ensure(h, h->col_d, (size_t)std::max<int64_t>(nnz, 1)));
   }
-  // Upload on a second stream, in minibatch order: [row_ptr] then the col range of every minibatch this rank
-  // trains, an event after each piece.  The compute stream waits per minibatch (train_epoch_impl), so the
-  // transfer of minibatch k + 1 rides under the kernels of minibatch k.  (The previous call ended with a
-  // synchronise of the compute stream, so nothing still reads the old device copy.)
+  // The upload runs on a second stream, one piece per minibatch this rank trains (its row_ptr range and its col
+  // range), an event after each piece; train_epoch_impl issues piece k right before it queues minibatch k's
+  // kernels, which wait for that event — the transfer of minibatch k + 1 rides under the kernels of minibatch
+  // k.  (The previous call ended with a synchronise of the compute stream, so nothing still reads the old copy.)
   if (!h->plan_valid) TRY(build_plan(h));
   if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   while (h->copy_ev.size() < h->plan.size() + 1) {
@@ -1041,32 +1051,9 @@ int cdae_train_epoch_csr(cdae_handle* h, const int64_t* row_ptr, const int32_t* 
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->copy_ev.push_back(e);
   }
-  if (h->world == 1) {
-    CU(cudaMemcpyAsync(h->row_ptr_d.p, row_ptr, sizeof(int64_t) * (h->U + 1), cudaMemcpyHostToDevice, h->copy_stream));
-    h->h2d += sizeof(int64_t) * (h->U + 1);
-  } else {
-    for (const MiniBatch& p : h->plan) {
-      if (p.n_users == 0) continue;
-      CU(cudaMemcpyAsync(h->row_ptr_d.p + p.uid0, row_ptr + p.uid0, sizeof(int64_t) * (p.n_users + 1), cudaMemcpyHostToDevice, h->copy_stream));
-      h->h2d += sizeof(int64_t) * (p.n_users + 1);
-    }
-  }
-  CU(cudaEventRecord(h->copy_ev[0], h->copy_stream));
-  {
-    size_t k = 0;
-    for (const MiniBatch& p : h->plan) {
-      ++k;
-      if (p.n_users > 0) {
-        const int64_t s0 = row_ptr[p.uid0], s1 = row_ptr[p.uid0 + p.n_users];
-        if (s1 > s0) CU(cudaMemcpyAsync(h->col_d.p + s0, col + s0, sizeof(int32_t) * (s1 - s0), cudaMemcpyHostToDevice, h->copy_stream));
-        h->h2d += sizeof(int32_t) * (s1 - s0);
-      }
-      CU(cudaEventRecord(h->copy_ev[k], h->copy_stream));
-    }
-  }
   h->csr_unchecked = true;
   h->csr_bad = false;
-  const int rc = train_epoch_impl(h, seed, epoch, stats);
+  const int rc = train_epoch_impl(h, seed, epoch, stats, row_ptr, col);
   if (rc != 0) cudaStreamSynchronize(h->copy_stream);   // the caller's buffers must not be read after an error return
   return rc;
 }
