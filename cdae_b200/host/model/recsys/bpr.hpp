@@ -34,20 +34,8 @@ struct BPRConfig {
 class BPR : public IMF {
  public:
   BPR(const BPRConfig& mcfg) {
-    learn_rate_ = mcfg.learn_rate;
-    beta_ = mcfg.beta;
-    lambda_ = mcfg.lambda;
-    num_dim_ = mcfg.num_dim;
-    num_neg_ = mcfg.num_neg;
-    using_bias_term_ = mcfg.using_bias_term;
-    using_adagrad_ = mcfg.using_adagrad;
-    loss_ = Loss::create(mcfg.lt);
-    penalty_ = Penalty::create(mcfg.pt);
-    LOG(INFO) << "BPR Model Configure: \n"
-              << "\t{lambda: " << lambda_ << "}, {Learn Rate: " << learn_rate_ << "}, {Beta " << beta_ << "}, "
-              << "{Loss: " << loss_->loss_type() << "}, {Penalty: " << penalty_->penalty_type() << "}\n"
-              << "\t{Dim: " << num_dim_ << "}, {BiasTerm: " << using_bias_term_ << "}, "
-              << "{Using AdaGrad: " << using_adagrad_ << "}, {Num Negative: " << num_neg_ << "}";
+    configure("BPR", mcfg.learn_rate, mcfg.beta, mcfg.lambda, mcfg.lt, mcfg.pt, mcfg.num_dim, mcfg.num_neg,
+              mcfg.using_bias_term, mcfg.using_adagrad);
   }
 
   void reset(const Data& data_set) {

@@ -45,20 +45,8 @@ struct IMFConfig {
 class IMF : public RecsysModelBase {
  public:
   IMF(const IMFConfig& mcfg) {
-    learn_rate_ = mcfg.learn_rate;
-    beta_ = mcfg.beta;
-    lambda_ = mcfg.lambda;
-    num_dim_ = mcfg.num_dim;
-    num_neg_ = mcfg.num_neg;
-    using_bias_term_ = mcfg.using_bias_term;
-    using_adagrad_ = mcfg.using_adagrad;
-    loss_ = Loss::create(mcfg.lt);
-    penalty_ = Penalty::create(mcfg.pt);
-    LOG(INFO) << "IMF Model Configure: \n"
-              << "\t{lambda: " << lambda_ << "}, {Learn Rate: " << learn_rate_ << "}, {Beta: " << beta_ << "}, "
-              << "{Loss: " << loss_->loss_type() << "}, {Penalty: " << penalty_->penalty_type() << "}\n"
-              << "\t{Dim: " << num_dim_ << "}, {BiasTerm: " << using_bias_term_ << "}, "
-              << "{Using AdaGrad: " << using_adagrad_ << "}, {Num Negative: " << num_neg_ << "}";
+    configure("IMF", mcfg.learn_rate, mcfg.beta, mcfg.lambda, mcfg.lt, mcfg.pt, mcfg.num_dim, mcfg.num_neg,
+              mcfg.using_bias_term, mcfg.using_adagrad);
   }
 
   IMF() = default;
@@ -141,6 +129,19 @@ class IMF : public RecsysModelBase {
   DMatrix get_item_vecs() { return as_matrix(iv_, num_items_); }
 
  protected:
+  // shared by IMF and BPR (whose config structs have the same fields): hyper-parameters, loss, penalty, log line
+  void configure(const char* name, double learn_rate, double beta, double lambda, LossType lt, PenaltyType pt,
+                 size_t num_dim, size_t num_neg, bool bias, bool adagrad) {
+    learn_rate_ = learn_rate; beta_ = beta; lambda_ = lambda;
+    num_dim_ = num_dim; num_neg_ = num_neg;
+    using_bias_term_ = bias; using_adagrad_ = adagrad;
+    loss_ = Loss::create(lt);
+    penalty_ = Penalty::create(pt);
+    LOG(INFO) << name << " Model Configure: {lambda: " << lambda_ << "}, {Learn Rate: " << learn_rate_ << "}, {Beta: " << beta_
+              << "}, {Loss: " << loss_->loss_type() << "}, {Penalty: " << penalty_->penalty_type() << "}, {Dim: " << num_dim_
+              << "}, {BiasTerm: " << using_bias_term_ << "}, {Using AdaGrad: " << using_adagrad_ << "}, {Num Negative: "
+              << num_neg_ << "}";
+  }
   // AdaGrad: acc += grad^2; returns grad / (beta + sqrt(acc))
   double scaled_by_history(double grad, double& acc) const {
     acc += grad * grad;
