@@ -461,12 +461,25 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt_in, const Samp
   } else {
     TRY(launch_decode(h, bt, true, sa));
   }
+  // hidden_backward (user rows, hidden bias) and scatter (encoder item rows) both consume HG + Z and write
+  // disjoint state: outside profiling they run side by side, hidden_backward on a second stream.
+  const bool side = !h->profiling && bt.n_users > 0;
+  if (side) {
+    if (!h->side_stream) {
+      CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&h->side_fork, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->side_join, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(h->side_fork, h->stream));
+    CU(cudaStreamWaitEvent(h->side_stream, h->side_fork, 0));
+  }
   if (bt.n_users > 0) {
     ProfScope ps(h, CDAE_K_HIDDEN_BWD);
     const int bx = h->ld / 4, by = std::max(1, 256 / bx);
-    hidden_backward_kernel<<<cdiv(bt.n_users, by), dim3(bx, by), sizeof(float4) * bx * by, h->stream>>>(h->m, bt, h->stats_d);
+    hidden_backward_kernel<<<cdiv(bt.n_users, by), dim3(bx, by), sizeof(float4) * bx * by, side ? h->side_stream : h->stream>>>(h->m, bt, h->stats_d);
     KERNEL_OK(h);
   }
+  if (side) CU(cudaEventRecord(h->side_join, h->side_stream));
   if (h->cfg.full_decode && !h->m.asym) {
     // tied weights: every item is an output of every user, so fd_gemm_kernel<.., true> already added
     // n*lambda*W[i]; an input item's occurrence merges into that one (cdae.hpp:249-250,342-343)
@@ -479,6 +492,7 @@ static int run_train_minibatch(cdae_handle* h, const BatchDev& bt_in, const Samp
   } else {
     TRY(launch_scatter(h, bt));
   }
+  if (side) CU(cudaStreamWaitEvent(h->stream, h->side_join, 0));
   if (h->m.linear_function && bt.n_users > 0) {
     uu_update_kernel<<<cdiv((int64_t)bt.n_users * h->ld, 256), 256, 0, h->stream>>>(h->m, bt, h->stats_d);
     KERNEL_OK(h);
@@ -800,6 +814,9 @@ int cdae_destroy(cdae_handle* h) {
   h->fd_zb.release(); h->fd_wb.release(); h->fd_g.release(); h->fd_bits.release(); h->fd_bias.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);
+  if (h->side_fork) cudaEventDestroy(h->side_fork);
+  if (h->side_join) cudaEventDestroy(h->side_join);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);

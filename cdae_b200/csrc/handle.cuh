@@ -67,6 +67,8 @@ struct cdae_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;      // cdae_train_epoch_csr: host -> device pieces, one event per minibatch
   std::vector<cudaEvent_t> copy_ev;
+  cudaStream_t side_stream = nullptr;      // hidden_backward_kernel runs here, beside scatter_kernel on `stream`
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cdae::ModelDev m;
   // item side: parameters, AdaGrad state and minibatch gradients as flat buffers of ONE layout

@@ -722,8 +722,8 @@ __global__ void __launch_bounds__(256) hidden_backward_kernel(ModelDev m, BatchD
       else dz = make_float4(1.f - zz.x * zz.x, 1.f - zz.y * zz.y, 1.f - zz.z * zz.z, 1.f - zz.w * zz.w);
     }
     d = mul4(hg, dz);
-    // pad columns: hg is exactly 0 there (W' pad columns are 0), so d is 0
-    st4(bt.D + (int64_t)u * m.ld + c, d);
+    // pad columns: hg is exactly 0 there (W' pad columns are 0), so d is 0.  (scatter_kernel forms the same
+    // delta itself from HG and Z, so nothing is stored here.)
     if (m.user_factor) {
       const int64_t uid = bt.uids[u];
       float* wp = m.Wu + uid * m.ld + c;
@@ -787,7 +787,18 @@ __global__ void __launch_bounds__(256) scatter_kernel(ModelDev m, BatchDev bt) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c = RM::col4(gl, v);
-    d[v] = ld4(bt.D + (int64_t)wi.u_local * m.ld + c);
+    // delta = hg (.) act'(z) (cdae.hpp:208-215, 295-301), formed here from HG and Z rather than read back from
+    // hidden_backward_kernel's D: the two kernels then have no dependency and run side by side (api.cu)
+    {
+      const float4 hgv = ld4(bt.HG + (int64_t)wi.u_local * m.ld + c);
+      const float4 zz = ld4(bt.Z + (int64_t)wi.u_local * m.ld + c);
+      float4 dz = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (!m.linear) {
+        if (!m.tanh_act) dz = make_float4(zz.x - zz.x * zz.x, zz.y - zz.y * zz.y, zz.z - zz.z * zz.z, zz.w - zz.w * zz.w);
+        else dz = make_float4(1.f - zz.x * zz.x, 1.f - zz.y * zz.y, 1.f - zz.z * zz.z, 1.f - zz.w * zz.w);
+      }
+      d[v] = mul4(hgv, dz);
+    }
     sd[v] = scale4(m.scale, d[v]);
     if (m.linear_function) sd[v] = mul4(ld4(m.Uu + (int64_t)wi.uid * m.ld + c), sd[v]);
     gu[v] = f4zero();
