@@ -1374,7 +1374,16 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
     return set_error(CDAE_E_INVALID, "bad argument");
   CU(cudaSetDevice(h->cfg.device));
   const int ld = h->ld;
-  float *src = nullptr, *dst = nullptr, *sink = nullptr;
+  struct Scratch {   // released on every return path (the CU macro returns early on a CUDA error)
+    float *src = nullptr, *dst = nullptr, *sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Scratch() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      cudaFree(src); cudaFree(dst); cudaFree(sink);
+    }
+  } sc;
+  float *&src = sc.src, *&dst = sc.dst, *&sink = sc.sink;
   const size_t bytes = sizeof(float) * (size_t)rows * ld;
   CU(cudaMalloc(&src, bytes));
   CU(cudaMalloc(&dst, bytes));
@@ -1385,7 +1394,7 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
   const uint32_t live_bytes = (uint32_t)((h->K * 4 + 15) / 16 * 16);   // modes 4, 5: bulk reductions of the real columns only
   const int n_warps = (int)((row_visits + rows_per_warp - 1) / rows_per_warp);
   const int grid = cdiv((int64_t)n_warps * 32, 256);
-  cudaEvent_t e0, e1;
+  cudaEvent_t &e0 = sc.e0, &e1 = sc.e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
   int rc = 0;
@@ -1409,8 +1418,6 @@ int cdae_probe_l2(cdae_handle* h, int64_t rows, int32_t mode, int64_t row_visits
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaEventElapsedTime(&ms, e0, e1));
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(src); cudaFree(dst); cudaFree(sink);
   if (rc) return rc;
   const double per = ms / reps;
   // modes 4 / 5 (bulk reductions, without / with the row loads) are reported in the same units as 2 / 3:

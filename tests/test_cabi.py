@@ -77,3 +77,36 @@ def test_sass_is_blackwell_native(built):
         assert op in sass, op
     assert "HMMA" not in sass.replace("UTCHMMA", "")            # no warp-level mma.sync anywhere
     assert ".STRONG.SYS" in sass                                # ld.acquire.sys / st.release.sys of the p2p flags
+
+
+def test_argument_checks_need_no_gpu(built):
+    """cdae_create range-checks the configuration (q in [0,1], finite lambda / lr, ...) — before any CUDA
+    call, so it is testable here; the group constructor checks its device count the same way."""
+    import ctypes as C
+    import numpy as np
+    from cdae_b200 import _lib
+    L = _lib.lib()
+    rp = np.array([0, 2, 4], np.int64)
+    col = np.array([0, 1, 1, 2], np.int32)
+    h = C.c_void_p()
+
+    def create(**kw):
+        c = _lib.Config()
+        assert L.cdae_config_default(C.byref(c)) == 0
+        c.loss_type = _lib.LOSS["CE"]
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return L.cdae_create(C.byref(c), 2, 3, rp.ctypes.data_as(_lib.i64p), col.ctypes.data_as(_lib.i32p), C.byref(h))
+
+    for bad in (dict(corruption_ratio=1.5), dict(corruption_ratio=-0.1), dict(corruption_ratio=float("nan")),
+                dict(lambda_=float("inf")), dict(lambda_=-1.0), dict(learn_rate=float("nan")), dict(beta=-1.0),
+                dict(num_dim=0), dict(num_dim=4096), dict(num_neg=-1), dict(loss_type=99)):
+        assert create(**bad) == -1, bad                                    # CDAE_E_INVALID
+        assert L.cdae_last_error()
+    bad_col = np.array([0, 1, 1, 7], np.int32)                              # item id 7 outside [0, 3)
+    c = _lib.Config()
+    L.cdae_config_default(C.byref(c))
+    assert L.cdae_create(C.byref(c), 2, 3, rp.ctypes.data_as(_lib.i64p), bad_col.ctypes.data_as(_lib.i32p), C.byref(h)) == -1
+    g = C.c_void_p()
+    for n in (0, 9):
+        assert L.cdae_group_create(C.byref(c), 2, 3, rp.ctypes.data_as(_lib.i64p), col.ctypes.data_as(_lib.i32p), None, n, C.byref(g)) == -1
