@@ -509,6 +509,7 @@ def topn_section(m, c, U, pk):
             "path": "tcgen05 bf16 + exact fp64 re-rank" if path == 1 else "fp32 CUDA cores",
             "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank", "topn_exact")) / reps / 1e3),
             "candidate_kernel_ms": ms, "verified_users": verified, "redone_exact_users": redone,
+            "probe_items": m.topn_probe_items(),               # > 0: sweep 1 started from probe thresholds (both launches are in candidate_kernel_ms)
             "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel<%d>" % (kp // 64),
                          "achieved": alg / (ms / 1e3) / 1e12 if ms > 0 else None, "peak": pk["tf_burst"],
                          "peak_source": pk["source"] + ", burst", "unit": "TFLOP/s",

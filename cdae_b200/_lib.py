@@ -64,6 +64,7 @@ SIGNATURES = {
     "cdae_topn_build": (C.c_int, [C.c_void_p, C.c_int32]),
     "cdae_topn_lookup": (C.c_int, [C.c_void_p, C.c_int64, i64p, f32p]),
     "cdae_topn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), i64p, i64p]),
+    "cdae_topn_probe_items": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "cdae_topn_fetch": (C.c_int, [C.c_void_p, i64p, f32p]),
     "cdae_topn_evaluate": (C.c_int, [C.c_void_p, i64p, i32p, f64p, i64p]),
     "cdae_dist_unique_id": (C.c_int, [C.c_void_p]),

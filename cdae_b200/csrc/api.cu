@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>   // topn probe pass: items ordered by mean-user score (topn_api.inl)
+
 #include "../../include/cdae_b200.h"
 #include "handle.cuh"
 #include "topn_kernels.cuh"
@@ -811,6 +813,8 @@ int cdae_destroy(cdae_handle* h) {
   h->test_rp_d.release(); h->test_col_d.release();
   h->tc_zb.release(); h->tc_wb.release(); h->tc_wmax.release(); h->tc_eps.release();
   h->tc_thr.release(); h->tc_redo.release(); h->tc_redo_thr.release();
+  h->tc_probe_wb.release(); h->tc_probe_keys.release(); h->tc_probe_ids.release(); h->tc_probe_pos.release();
+  h->tc_probe_bits.release(); h->tc_probe_thr.release(); h->tc_probe_zsum.release(); h->tc_probe_tmp.release();
   h->fd_zb.release(); h->fd_wb.release(); h->fd_g.release(); h->fd_bits.release(); h->fd_bias.release();
   if (h->stats_d) cudaFree(h->stats_d);
   if (h->stats_h) cudaFreeHost(h->stats_h);

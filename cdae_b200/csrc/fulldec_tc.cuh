@@ -173,6 +173,11 @@ __device__ __forceinline__ float sigmoid_sfu(float y) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + ex2_approx(-1.4426950408889634f * y)));
   return r;
 }
+#ifndef FD_EPI
+#define FD_EPI 0       // fd_score_kernel epilogue loop: 0 one 32-column TMEM load at a time; 1 the same with the waits moved under
+                       // the arithmetic; 2 16-column loads, one always in flight; 3 = 2 + next tile / target words fetched ahead
+                       // (A/B: CDAE_NVCC_FLAGS=-DFD_EPI=n)
+#endif
 #ifndef FD_SIGMOID
 #define FD_SIGMOID 2   // 0: polynomial on the FMA pipe, 1: SFU reciprocal, 2: alternate pairs, 3: 3 of 4 pairs on the SFU, 4: 1 of 4
                        // (A/B: CDAE_NVCC_FLAGS=-DFD_SIGMOID=n)
@@ -251,6 +256,77 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&v)[32], uint32_t pos
   uint32_t o[16];
   grad_compute<LT, BOUT>(v, pos, valid, row_ok, o, bias);
   grad_store(o, srow, cbase, sw);
+}
+
+// The same arithmetic for a chunk of N = 16 or 32 columns (FD_EPI >= 2: 16-column chunks, two TMEM loads in
+// flight).  pos / valid hold the chunk's N bits in their low bits.  The sigma path of a pair depends on
+// (j & 2) / (j & 6) only, so a 16-column chunk that starts at a multiple of 16 takes, score by score, the
+// path the 32-column form takes.
+template <int LT, bool BOUT, int N>
+__device__ __forceinline__ void grad_compute_n(const uint32_t (&v)[N], uint32_t pos, uint32_t valid, bool row_ok,
+                                               uint32_t (&o)[N / 2], const float* bias = nullptr) {
+  constexpr uint32_t FULL = N == 32 ? 0xffffffffu : ((1u << (N & 31)) - 1u);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    float y0 = __uint_as_float(v[j]), y1 = __uint_as_float(v[j + 1]);
+    if (BOUT) {
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + j));
+      y0 += b.x;
+      y1 += b.y;
+    }
+    const float t0 = __uint_as_float(((pos >> j) & 1u) * 0x3f800000u);
+    const float t1 = __uint_as_float(((pos >> (j + 1)) & 1u) * 0x3f800000u);
+    float g0, g1;
+    if (LT == LOSS_CE) {
+      if (FD_SIGMOID == 1 || (FD_SIGMOID == 2 && (j & 2)) || (FD_SIGMOID == 3 && (j & 6)) || (FD_SIGMOID == 4 && !(j & 6))) {
+        g0 = sigmoid_sfu(y0);
+        g1 = sigmoid_sfu(y1);
+      } else {
+        sigmoid2(y0, y1, g0, g1);
+      }
+      g0 -= t0;
+      g1 -= t1;
+    } else {
+      g0 = 2.f * (y0 - t0);
+      g1 = 2.f * (y1 - t1);
+    }
+    o[j >> 1] = pack_bf16x2(g0, g1);
+  }
+  if ((valid & FULL) != FULL) {      // warp-uniform: only the padded tail of the last tile
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      if (!((valid >> (2 * j)) & 1u)) o[j] &= 0xffff0000u;
+      if (!((valid >> (2 * j + 1)) & 1u)) o[j] &= 0x0000ffffu;
+    }
+  }
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) o[j] = 0u;
+  }
+}
+// NW packed words = NW / 4 16-byte pieces of this thread's staging row, starting at piece p0
+template <int NW>
+__device__ __forceinline__ void grad_store_n(const uint32_t (&o)[NW], unsigned char* srow, int p0, int sw) {
+#pragma unroll
+  for (int j = 0; j < NW / 4; ++j)
+    *reinterpret_cast<uint4*>(srow + (((p0 + j) ^ sw) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane (tcgen05.ld 32x32b.x16) and the matching wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -411,6 +487,7 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
     // are fetched at the END of tile t's work (a load issued before the current words are consumed
     // would share their scoreboard and stall the consumer)
     const uint2* brow = reinterpret_cast<const uint2*>(a.bits + (int64_t)(u0 + row) * (a.I_pad / 32)) + (int64_t)t_lo * 4 + h;
+#if FD_EPI == 0
     uint2 nb = make_uint2(0u, 0u);
     if (n_t > 0) nb = __ldg(brow);
     for (int t = 0; t < n_t; ++t) {
@@ -449,6 +526,136 @@ __global__ void __launch_bounds__(640, 1) fd_score_kernel(const __grid_constant_
       }
       if (t + 1 < n_t) nb = __ldg(brow + 4 * (t + 1));
     }
+#elif FD_EPI == 1
+    // As FD_EPI = 0, but nothing of the tile's work waits behind the TMA engine: the wait for "the previous
+    // tile's store has read the staging tile" sits between the first chunk's arithmetic and its stores, and
+    // the second TMEM load is issued before it, so both latencies run under each other.
+    uint2 nb = make_uint2(0u, 0u);
+    if (n_t > 0) nb = __ldg(brow);
+    for (int t = 0; t < n_t; ++t) {
+      const int buf = t & 1;
+      const uint32_t par = (t >> 1) & 1;
+      const uint2 cb = nb;
+      const int64_t item0 = (int64_t)(t_lo + t) * TILE_I + h * 64;
+      const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I + h * 64);
+      mbar_wait(t_full + buf, par);
+      tc_fence_after();
+      uint32_t v[32], o[16];
+      tmem_ld32_issue(col0, v);
+      tmem_ld_wait(v);
+      {
+        const uint32_t valid = item0 + 32 <= a.I ? 0xffffffffu : (item0 >= a.I ? 0u : ((1u << (int)(a.I - item0)) - 1u));
+        grad_compute<LT, BOUT>(v, cb.x, valid, row_ok, o, a.bias + item0);
+      }
+      tmem_ld32_issue(col0 + 32u, v);
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      grad_store(o, srow, 0, sw);
+      tmem_ld_wait(v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + buf);   // this warp's TMEM columns are in registers
+      {
+        const int64_t first = item0 + 32;
+        const uint32_t valid = first + 32 <= a.I ? 0xffffffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+        grad_compute<LT, BOUT>(v, cb.y, valid, row_ok, o, a.bias + first);
+        grad_store(o, srow, 4, sw);
+      }
+      fence_proxy_async();                         // staging writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_g, stg, (int)item0, u0 + q * 32);
+        bulk_commit();
+      }
+      if (t + 1 < n_t) nb = __ldg(brow + 4 * (t + 1));
+    }
+#else
+    // FD_EPI = 2: the tile's 64 columns are read in four 16-column TMEM loads, always one in flight under
+    // the arithmetic of the previous chunk (registers: two 16-word buffers instead of one 32-word buffer), and
+    // the wait for the staging tile sits between the first chunk's arithmetic and its stores.
+    // FD_EPI = 3: in addition the first TMEM load of tile t + 1 is issued before the last chunk of tile t is
+    // worked on, and the target words are fetched two tiles ahead.
+    constexpr bool AHEAD = FD_EPI >= 3;
+    uint2 nb = make_uint2(0u, 0u), nb2 = make_uint2(0u, 0u);
+    if (n_t > 0) nb = __ldg(brow);
+    if (AHEAD && n_t > 1) nb2 = __ldg(brow + 4);
+    uint32_t va[16], vb[16];
+    if (AHEAD && n_t > 0) {
+      mbar_wait(t_full + 0, 0u);
+      tc_fence_after();
+      tmem_ld16_issue(lane_addr + (uint32_t)(h * 64), va);
+    }
+    for (int t = 0; t < n_t; ++t) {
+      const int buf = t & 1;
+      const uint32_t par = (t >> 1) & 1;
+      const uint2 cb = nb;
+      const int64_t item0 = (int64_t)(t_lo + t) * TILE_I + h * 64;
+      const uint32_t col0 = lane_addr + (uint32_t)(buf * TILE_I + h * 64);
+      if (!AHEAD) {
+        mbar_wait(t_full + buf, par);
+        tc_fence_after();
+        tmem_ld16_issue(col0, va);
+      }
+      tmem_ld_wait16(va);
+      tmem_ld16_issue(col0 + 16u, vb);
+      {
+        const uint32_t valid = item0 + 16 <= a.I ? 0xffffu : (item0 >= a.I ? 0u : ((1u << (int)(a.I - item0)) - 1u));
+        uint32_t o[8];
+        grad_compute_n<LT, BOUT, 16>(va, cb.x & 0xffffu, valid, row_ok, o, a.bias + item0);
+        // the TMA store of the previous tile must have read the staging tile before it is rewritten
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        grad_store_n<8>(o, srow, 0, sw);
+      }
+      tmem_ld_wait16(vb);
+      tmem_ld16_issue(col0 + 32u, va);
+      {
+        const int64_t first = item0 + 16;
+        const uint32_t valid = first + 16 <= a.I ? 0xffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+        uint32_t o[8];
+        grad_compute_n<LT, BOUT, 16>(vb, cb.x >> 16, valid, row_ok, o, a.bias + first);
+        grad_store_n<8>(o, srow, 2, sw);
+      }
+      tmem_ld_wait16(va);
+      tmem_ld16_issue(col0 + 48u, vb);
+      {
+        const int64_t first = item0 + 32;
+        const uint32_t valid = first + 16 <= a.I ? 0xffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+        uint32_t o[8];
+        grad_compute_n<LT, BOUT, 16>(va, cb.y & 0xffffu, valid, row_ok, o, a.bias + first);
+        grad_store_n<8>(o, srow, 4, sw);
+      }
+      tmem_ld_wait16(vb);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + buf);   // this warp's TMEM columns are in registers
+      if (AHEAD && t + 1 < n_t) {                  // va is free: the first chunk of the next tile
+        mbar_wait(t_full + (buf ^ 1), (uint32_t)(((t + 1) >> 1) & 1));
+        tc_fence_after();
+        tmem_ld16_issue(lane_addr + (uint32_t)((buf ^ 1) * TILE_I + h * 64), va);
+      }
+      {
+        const int64_t first = item0 + 48;
+        const uint32_t valid = first + 16 <= a.I ? 0xffffu : (first >= a.I ? 0u : ((1u << (int)(a.I - first)) - 1u));
+        uint32_t o[8];
+        grad_compute_n<LT, BOUT, 16>(vb, cb.y >> 16, valid, row_ok, o, a.bias + first);
+        grad_store_n<8>(o, srow, 6, sw);
+      }
+      fence_proxy_async();                         // staging writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_g, stg, (int)item0, u0 + q * 32);
+        bulk_commit();
+      }
+      if (AHEAD) {
+        nb = nb2;
+        if (t + 2 < n_t) nb2 = __ldg(brow + 4 * (t + 2));
+      } else if (t + 1 < n_t) {
+        nb = __ldg(brow + 4 * (t + 1));
+      }
+    }
+    if (AHEAD && n_t > 0) tmem_ld_wait16(va);      // (nothing outstanding; keeps va's last definition consumed)
+#endif
     if (lane == 0) bulk_wait0();
   }
 

@@ -121,6 +121,16 @@ struct cdae_handle {
   cdae::DevBuf<float> tc_redo_thr;       // start threshold of each user of sweep 2
   const int32_t* tc_exact_list = nullptr;  // users left for the exact kernel (inside tc_redo)
   int64_t topn_pass2_users = 0;          // users that needed the second tensor sweep
+  // probe pass (start thresholds of sweep 1 from the M items with the largest mean-user score)
+  cdae::DevBuf<uint16_t> tc_probe_wb;    // [M][Kp] packed rows of the probe items
+  cdae::DevBuf<float> tc_probe_keys;     // [2 I] sort keys in / out
+  cdae::DevBuf<int32_t> tc_probe_ids;    // [2 I] item ids in / out (sorted by key, descending)
+  cdae::DevBuf<int32_t> tc_probe_pos;    // [I] row of an item in the probe table, -1 = not in it
+  cdae::DevBuf<uint32_t> tc_probe_bits;  // [users_pad][M / 32] rated bitmap over the probe table
+  cdae::DevBuf<float> tc_probe_thr;      // [users] start thresholds
+  cdae::DevBuf<float> tc_probe_zsum;     // [ld] column sums of the hidden vectors
+  cdae::DevBuf<unsigned char> tc_probe_tmp;  // radix-sort scratch
+  int topn_probe_items = 0;              // last cdae_topn_build: size of the probe table (0 = no probe pass)
   int64_t topn_tc_users = 0, topn_redo_users = 0;  // last cdae_topn_build: verified on the tensor path / redone exactly
   int topn_path = 0;                     // 0 fp32 CUDA cores, 1 tcgen05
   // full-item-decode training (fulldec_tc.cuh): bf16 operands and the loss-gradient matrix

@@ -70,7 +70,8 @@ static int tc_launch(cdae_handle* h, const CUtensorMap& ma, const CUtensorMap& m
 // are written to redo_list[0 .. *n_redo) together with a start threshold for a second sweep.
 // Wb (the packed item side) must already be in h->tc_wb; init_thr is nullable.
 static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users, int topk,
-                   const float* init_thr, int32_t* redo_list, float* redo_thr, int* redo_cnt, int* n_redo) {
+                   const float* init_thr, int32_t* redo_list, float* redo_thr, int* redo_cnt, int* n_redo,
+                   bool allow_split = true) {
   const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
   const int64_t n_pad = round_up(n_users, tc::TILE_U), I_pad = round_up(h->I, tc::TILE_I);
   TRY(ensure(h, h->tc_zb, (size_t)(n_pad * Kp)));
@@ -112,7 +113,8 @@ static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_
   // Item ranges: a sweep that starts from known thresholds (init_thr) is paced by the MMA, not by
   // candidate handling, and has few user tiles — cut the items into ranges while the grid still fits one wave.
   int S = 1;
-  if (init_thr) while (S < 8 && grid * S * 2 <= h->sm_count && a.n_tiles / (S * 2) >= 8) S *= 2;
+  // (not for a first sweep that starts from probe thresholds: its candidate lists need whole segments)
+  if (init_thr && allow_split) while (S < 8 && grid * S * 2 <= h->sm_count && a.n_tiles / (S * 2) >= 8) S *= 2;
   a.n_splits = S;
   a.tiles_per_split = (a.n_tiles + S - 1) / S;
   a.seg = tc::CAND_MAX / S;
@@ -140,6 +142,101 @@ static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_
   }
   CU(cudaMemcpyAsync(n_redo, redo_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Probe pass (topn_tc.cuh, "Probe pass"): start thresholds for sweep 1 from the M items with the largest
+// mean-user score.  Leaves them in h->tc_probe_thr (one per user of the list) and returns M in *m_out, or
+// *m_out = 0 when the item table is too small for a probe to pay (fewer than 512 items) or
+// CDAE_B200_TOPN_PROBE=0.  h->tc_wb must hold the packed item side.
+#ifndef TOPN_PROBE_DEFAULT
+#define TOPN_PROBE_DEFAULT 0
+#endif
+static int tc_probe_thresholds(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users, int topk, int* m_out) {
+  *m_out = 0;
+  const char* env = getenv("CDAE_B200_TOPN_PROBE");   // read per call: tests switch it inside one process
+  const bool on = env ? atoi(env) != 0 : TOPN_PROBE_DEFAULT != 0;
+  if (!on || h->I < 512 || n_users <= 0 || h->I >= 0x7fffffff) return 0;
+  const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
+  const int M = tc::TILE_I * (int)std::min<int64_t>(4, std::max<int64_t>(1, h->I / 2048));   // 256 .. 1024, <= I / 2
+  const int64_t n_pad = round_up(n_users, tc::TILE_U);
+  const int64_t words = M / 32;
+  const int I = (int)h->I;
+  TRY(ensure(h, h->tc_probe_zsum, (size_t)h->ld));
+  TRY(ensure(h, h->tc_probe_keys, (size_t)(2 * h->I)));
+  TRY(ensure(h, h->tc_probe_ids, (size_t)(2 * h->I)));
+  TRY(ensure(h, h->tc_probe_pos, (size_t)h->I));
+  TRY(ensure(h, h->tc_probe_wb, (size_t)M * Kp));
+  TRY(ensure(h, h->tc_probe_bits, (size_t)(n_pad * words)));
+  TRY(ensure(h, h->tc_probe_thr, (size_t)n_users));
+  TRY(ensure(h, h->tc_zb, (size_t)(n_pad * Kp)));
+  float* keys_in = h->tc_probe_keys.p;
+  float* keys_out = h->tc_probe_keys.p + h->I;
+  int32_t* ids_in = h->tc_probe_ids.p;
+  int32_t* ids_out = h->tc_probe_ids.p + h->I;
+  size_t tmp_bytes = 0;
+  if (cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, keys_in, keys_out, ids_in, ids_out, I, 0, 32, h->stream) != cudaSuccess)
+    return set_error(CDAE_E_CUDA, "radix sort (size query) failed");
+  TRY(ensure(h, h->tc_probe_tmp, std::max<size_t>(tmp_bytes, 16)));
+  {
+    ProfScope ps(h, CDAE_K_TOPN_PACK);
+    CU(cudaMemsetAsync(h->tc_probe_zsum.p, 0, sizeof(float) * h->ld, h->stream));
+    const int upb = 64;
+    tc::probe_colsum_kernel<<<cdiv(n_users, upb), 256, 0, h->stream>>>(h->topn_z.p, users, (int)n_users, h->ld, upb, h->tc_probe_zsum.p);
+    KERNEL_OK(h);
+    tc::probe_key_kernel<<<cdiv(h->I * 32, 256), 256, 0, h->stream>>>(Wd, h->m.bp, h->I, K, h->ld, h->tc_probe_zsum.p,
+                                                                      1.f / (float)n_users, keys_in, ids_in);
+    KERNEL_OK(h);
+    tmp_bytes = h->tc_probe_tmp.cap;
+    if (cub::DeviceRadixSort::SortPairsDescending(h->tc_probe_tmp.p, tmp_bytes, keys_in, keys_out, ids_in, ids_out, I, 0, 32, h->stream) != cudaSuccess)
+      return set_error(CDAE_E_CUDA, "radix sort failed");
+    CU(cudaMemsetAsync(h->tc_probe_pos.p, 0xff, sizeof(int32_t) * h->I, h->stream));
+    tc::probe_pos_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(ids_out, M, h->tc_probe_pos.p);
+    KERNEL_OK(h);
+    tc::probe_gather_w_kernel<<<cdiv((int64_t)M * (Kp / 8), 256), 256, 0, h->stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h->tc_wb.p), ids_out, M, Kp, reinterpret_cast<__nv_bfloat16*>(h->tc_probe_wb.p));
+    KERNEL_OK(h);
+    CU(cudaMemsetAsync(h->tc_probe_bits.p, 0, sizeof(uint32_t) * (size_t)(n_pad * words), h->stream));
+    tc::probe_bitmap_kernel<<<cdiv(n_users * 32, 256), 256, 0, h->stream>>>(users, (int)n_users, h->row_ptr_d.p, h->col_d.p,
+                                                                           h->tc_probe_pos.p, words, h->tc_probe_bits.p);
+    KERNEL_OK(h);
+    tc::pack_z_bf16_kernel<<<cdiv(n_pad * 32, 256), 256, 0, h->stream>>>(
+        h->topn_z.p, users, (int)n_users, n_pad, K, h->ld, Kp, h->tc_wmax.p,
+        reinterpret_cast<__nv_bfloat16*>(h->tc_zb.p), h->tc_eps.p);
+    KERNEL_OK(h);
+  }
+  alignas(64) CUtensorMap ma, mb;
+  TRY(tc_make_map(&ma, h->tc_zb.p, (uint64_t)n_pad, (uint64_t)Kp, tc::TILE_U));
+  TRY(tc_make_map(&mb, h->tc_probe_wb.p, (uint64_t)M, (uint64_t)Kp, tc::TILE_I));
+  tc::TcArgs a;
+  a.n_users = (int)n_users; a.I = M; a.n_tiles = M / tc::TILE_I;
+  a.users = users; a.row_ptr = h->row_ptr_d.p; a.col = h->col_d.p;
+  a.cand_id = h->cand_id.p; a.cand_s = h->cand_s.p; a.cand_cnt = h->cand_cnt.p; a.cand_thr = h->tc_thr.p;
+  a.init_thr = nullptr;
+  a.bits = h->tc_probe_bits.p;
+  a.words = words;
+  a.n_splits = 1;
+  a.tiles_per_split = a.n_tiles;
+  a.seg = tc::CAND_MAX;
+  const int grid = (int)(n_pad / tc::TILE_U);
+  {
+    ProfScope ps(h, CDAE_K_TOPN);
+    switch (KB) {
+      case 1: TRY(tc_launch<1>(h, ma, mb, a, grid)); break;
+      case 2: TRY(tc_launch<2>(h, ma, mb, a, grid)); break;
+      case 3: TRY(tc_launch<3>(h, ma, mb, a, grid)); break;
+      case 4: TRY(tc_launch<4>(h, ma, mb, a, grid)); break;
+      default: TRY(tc_launch<5>(h, ma, mb, a, grid)); break;
+    }
+    KERNEL_OK(h);
+  }
+  {
+    ProfScope ps(h, CDAE_K_TOPN_PACK);
+    tc::probe_thr_kernel<<<cdiv(n_users, 256), 256, 0, h->stream>>>(h->cand_s.p, h->cand_cnt.p, h->tc_eps.p, (int)n_users,
+                                                                    a.seg, topk, h->tc_probe_thr.p);
+    KERNEL_OK(h);
+  }
+  *m_out = M;
   return 0;
 }
 
@@ -173,8 +270,11 @@ static int topn_candidates_tc(cdae_handle* h, const float* Wd, const int32_t* us
         Wd, h->m.bp, h->I, I_pad, K, h->ld, Kp, reinterpret_cast<__nv_bfloat16*>(h->tc_wb.p));
     KERNEL_OK(h);
   }
-  int n1 = 0;
-  TRY(tc_pass(h, Wd, users, n_users, topk, nullptr, redo1, h->tc_redo_thr.p, redo_cnt, &n1));
+  int n1 = 0, probe_m = 0;
+  TRY(tc_probe_thresholds(h, Wd, users, n_users, topk, &probe_m));
+  h->topn_probe_items = probe_m;
+  TRY(tc_pass(h, Wd, users, n_users, topk, probe_m > 0 ? h->tc_probe_thr.p : nullptr, redo1, h->tc_redo_thr.p, redo_cnt, &n1,
+              /*allow_split=*/false));
   h->topn_pass2_users = n1;
   *n_redo = n1;
   h->tc_exact_list = redo1;
@@ -213,6 +313,7 @@ int cdae_topn_build(cdae_handle* h, int32_t topk) {
   const float* Wd = h->m.asym ? h->m.V : h->m.W;
   h->topn_tc_users = h->topn_redo_users = 0;
   h->topn_path = 0;
+  h->topn_probe_items = 0;
   const int32_t* exact_users = users;
   int64_t n_exact = n_users;
   if (n_users > 0 && tc_path_wanted(h, topk)) {
@@ -254,6 +355,12 @@ int cdae_topn_stats(cdae_handle* h, int32_t* path, int64_t* verified_users, int6
   if (path) *path = h->topn_path;
   if (verified_users) *verified_users = h->topn_tc_users;
   if (redone_users) *redone_users = h->topn_redo_users;
+  return 0;
+}
+
+int cdae_topn_probe_items(cdae_handle* h, int32_t* items_out) {
+  if (!h || !items_out) return set_error(CDAE_E_INVALID, "NULL argument");
+  *items_out = h->topn_probe_items;
   return 0;
 }
 

@@ -314,6 +314,110 @@ __global__ void __launch_bounds__(256) topn_bitmap_kernel(const int32_t* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Probe pass (cdae_topn_build, tensor-core path).  A sweep that starts from thr = -inf appends ~k ln(I/k)
+// candidates per user before its threshold settles (about 220 at config B: nearly every 32-column chunk of
+// every warp takes the slow append path, and that — not the MMA — is what the sweep costs).  The items that
+// can reach a top-k list are few and largely the same for everybody (high output bias, high score for the
+// AVERAGE user), so the build first scores every user against the M items with the largest mean-user score
+// z_mean.W'[i] + b'[i] (M = 256..1024, one to four tiles) with the same kernel, takes the k-th best
+// approximate score a_k of that pass and starts the real sweep at
+//     thr0 = a_k - 2 eps_u - tiny:
+// k unrated items have exact score >= a_k - eps_u, so an item with approx <= thr0 has exact
+// <= thr0 + eps_u < (k-th best exact score) and cannot be in the list; the verification of the re-rank
+// (thr_u + eps_u < k-th best exact) holds for thr0 by construction.  Nothing about the final lists depends
+// on the probe being good: a poor probe only means a lower start threshold.
+__global__ void __launch_bounds__(256) probe_colsum_kernel(const float* __restrict__ Z, const int32_t* __restrict__ users,
+                                                           int n, int ld, int users_per_block, float* __restrict__ out) {
+  const int r0 = blockIdx.x * users_per_block, r1 = min(n, r0 + users_per_block);
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += Z[(int64_t)(users ? users[r] : r) * ld + c];
+    atomicAdd(out + c, s);
+  }
+}
+// key[i] = b'[i] + W'[i].zsum * inv_n, ids[i] = i; one warp per item
+__global__ void __launch_bounds__(256) probe_key_kernel(const float* __restrict__ W, const float* __restrict__ bp, int64_t I,
+                                                        int K, int ld, const float* __restrict__ zsum, float inv_n,
+                                                        float* __restrict__ keys, int32_t* __restrict__ ids) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= I) return;
+  float s = 0.f;
+  for (int c = lane; c < K; c += 32) s = fmaf(W[i * ld + c], zsum[c], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    const float k = fmaf(s, inv_n, bp[i]);
+    keys[i] = k == k ? k : -INFINITY;   // (a NaN key would poison the sort order)
+    ids[i] = (int32_t)i;
+  }
+}
+// pos_of[item] = its row in the probe table (pos_of is preset to -1)
+__global__ void __launch_bounds__(256) probe_pos_kernel(const int32_t* __restrict__ sorted_ids, int M, int32_t* __restrict__ pos_of) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < M) pos_of[sorted_ids[p]] = p;
+}
+// probe table: row p = packed row of item sorted_ids[p]; one thread per 16 bytes
+__global__ void __launch_bounds__(256) probe_gather_w_kernel(const __nv_bfloat16* __restrict__ wb, const int32_t* __restrict__ sorted_ids,
+                                                             int M, int Kp, __nv_bfloat16* __restrict__ out) {
+  const int g8 = Kp / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * g8) return;
+  const int p = (int)(idx / g8), c0 = (int)(idx % g8) * 8;
+  *reinterpret_cast<uint4*>(out + (int64_t)p * Kp + c0) =
+      *reinterpret_cast<const uint4*>(wb + (int64_t)sorted_ids[p] * Kp + c0);
+}
+// rated bitmap over the probe table's rows: bit p of row r <=> probe item p is in the train row of user r
+__global__ void __launch_bounds__(256) probe_bitmap_kernel(const int32_t* __restrict__ users, int n,
+                                                           const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                           const int32_t* __restrict__ pos_of, int64_t words,
+                                                           uint32_t* __restrict__ bits) {
+  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const int64_t uid = users ? users[r] : r;
+  const int64_t p0 = row_ptr[uid], p1 = row_ptr[uid + 1];
+  uint32_t* row = bits + (int64_t)r * words;
+  for (int64_t p = p0 + lane; p < p1; p += 32) {
+    const int q = __ldg(pos_of + __ldg(col + p));
+    if (q >= 0) atomicOr(row + (q >> 5), 1u << (q & 31));
+  }
+}
+// thr0[r] = (k-th largest approximate score of user r's probe candidates) - 2 eps_r - tiny, or -inf when the
+// probe pass holds fewer than k candidates for the user.  One thread per user.
+__global__ void __launch_bounds__(256) probe_thr_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_cnt,
+                                                        const float* __restrict__ eps, int n, int seg, int topk,
+                                                        float* __restrict__ thr0) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int cnt = cand_cnt[r];
+  float out = -INFINITY;
+  if (cnt >= topk) {
+    // k-th largest by repeated "largest value below the previous one" (at most k passes over <= CAND_MAX entries)
+    const float* s = cand_s + (int64_t)r * seg;
+    float prev = INFINITY, kth = -INFINITY;
+    int seen = 0;
+    for (int pass = 0; pass < topk && seen < topk; ++pass) {
+      float m = -INFINITY;
+      int c = 0;
+      for (int x = 0; x < cnt; ++x) {
+        const float v = s[x];
+        if (v < prev) {
+          if (v > m) { m = v; c = 1; }
+          else if (v == m) ++c;
+        }
+      }
+      if (c == 0) break;
+      seen += c;
+      prev = m;
+      kth = m;
+    }
+    if (seen >= topk && kth > -INFINITY) out = kth - 2.f * eps[r] - 1e-6f * fabsf(kth) - 1e-30f;
+  }
+  thr0[r] = out;
+}
+
 // Compaction of the per-user candidate buffers, called by a whole epilogue warp with every lane
 // working on its own row: raise thr to a value t with KEEP_LO <= #{s > t} <= KEEP_HI (bisection on
 // the value) and drop the entries <= t.  thr never decreases, so "every non-candidate has

@@ -899,19 +899,19 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_cnt / 4; i += (int64_t)gridDim.x * blockDim.x)
     st4(a.cnt_clear + i * 4, f4zero());
+  // Two elements per thread and pass, and the weight / accumulator loads issued TOGETHER with the gradient load
+  // (nearly every row of a minibatch is touched, so they are almost never wasted): one L2 round trip per pass
+  // instead of "gradient, then — if non-zero — weight and accumulator".
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int s = 0; s < a.nseg; ++s) {
     const ApplySeg sg = a.seg[s];
     const float extra = sg.extra_coef * steps;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n4;
-         i += (int64_t)gridDim.x * blockDim.x) {
-      float4 g4 = ld4(sg.g + i * 4);
-      const float rowc = sg.cnt ? sg.cnt_coef * __ldg(sg.cnt + i / sg.ld4) : 0.f;
-      if (extra == 0.f && rowc == 0.f && g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) continue;
+    auto finish = [&](int64_t i, float4 g4, float4 w4, float4 a4, float rowc) {
+      if (extra == 0.f && rowc == 0.f && g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) return;
       if (discard) {
         st4(sg.g + i * 4, f4zero());
-        continue;
+        return;
       }
-      float4 w4 = ld4(sg.w + i * 4);
       float g[4] = {g4.x, g4.y, g4.z, g4.w};
       float w[4] = {w4.x, w4.y, w4.z, w4.w};
       const float lin = extra + rowc;
@@ -920,7 +920,6 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
         for (int k = 0; k < 4; ++k) g[k] += lin * w[k];
       }
       if (a.adagrad) {
-        float4 a4 = ld4(sg.acc + i * 4);
         float ac[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -934,6 +933,23 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
       for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
       st4(sg.w + i * 4, make_float4(w[0], w[1], w[2], w[3]));
       st4(sg.g + i * 4, f4zero());
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n4; i += 2 * stride) {
+      const int64_t j = i + stride;
+      const bool two = j < sg.n4;
+      const float4 gi = ld4(sg.g + i * 4), wi = ld4(sg.w + i * 4);
+      const float4 ai = a.adagrad ? ld4(sg.acc + i * 4) : f4zero();
+      const float ci = sg.cnt ? sg.cnt_coef * __ldg(sg.cnt + i / sg.ld4) : 0.f;
+      float4 gj = f4zero(), wj = f4zero(), aj = f4zero();
+      float cj = 0.f;
+      if (two) {
+        gj = ld4(sg.g + j * 4);
+        wj = ld4(sg.w + j * 4);
+        if (a.adagrad) aj = ld4(sg.acc + j * 4);
+        if (sg.cnt) cj = sg.cnt_coef * __ldg(sg.cnt + j / sg.ld4);
+      }
+      finish(i, gi, wi, ai, ci);
+      if (two) finish(j, gj, wj, aj, cj);
     }
   }
 }

@@ -258,6 +258,12 @@ class CDAE:
         _lib.check(self._L.cdae_topn_stats(self._h, C.byref(p), C.byref(a), C.byref(b)))
         return p.value, a.value, b.value
 
+    def topn_probe_items(self):
+        """Items in the probe table of the last pre_recommend (0 = the first sweep started from -inf)."""
+        n = C.c_int32()
+        _lib.check(self._L.cdae_topn_probe_items(self._h, C.byref(n)))
+        return n.value
+
     def topn_evaluate(self, test_row_ptr, test_col):
         """TOPN_Evaluation::evaluate on the stored lists: [P@1,P@5,P@10,R@1,R@5,R@10,MAP@5,MAP@10]."""
         rp = _arr(test_row_ptr, np.int64)

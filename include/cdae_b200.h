@@ -183,6 +183,11 @@ int cdae_topn_lookup(cdae_handle* h, int64_t uid, int64_t* ids_out, float* score
  * recomputed by the exact fp32 kernel; path 0 = fp32 kernel for everyone (K > 318, topk > 16, or
  * CDAE_B200_TOPN=fp32 in the environment). */
 int cdae_topn_stats(cdae_handle* h, int32_t* path, int64_t* verified_users, int64_t* redone_users);
+/* Size of the probe table of the last cdae_topn_build (tensor path): the first sweep started from per-user
+ * thresholds derived from the items with the largest mean-user score; 0 = no probe pass (fewer than 512
+ * items, the fp32 path, or switched off with CDAE_B200_TOPN_PROBE=0).  Only the cost of the build depends on
+ * it — every list is verified or recomputed exactly either way. */
+int cdae_topn_probe_items(cdae_handle* h, int32_t* items_out);
 /* Whole table, U x topk (ids) and U x topk (scores; nullable). */
 int cdae_topn_fetch(cdae_handle* h, int64_t* ids_out, float* scores_out);
 /* TOPN_Evaluation::evaluate (evaluation.hpp:113-181) on the built table against a test CSR:
