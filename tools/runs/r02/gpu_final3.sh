@@ -6,10 +6,11 @@
 mkdir -p gpurun_out
 T0=$(date +%s)
 left() { local l=$(( 262 - ($(date +%s) - T0) )); [ $l -lt 1 ] && l=1; echo $l; }
+make -s -C oracle all > gpurun_out/g_make.log 2>&1   # once, before five processes would race to do it
 python tools/final_ab.py gen C E B > gpurun_out/g_gen.log 2>&1 &
-(timeout 150 python -m pytest tests -m gpu -x -q > gpurun_out/g_pytest.log 2>&1; echo "pytest default rc $?" > gpurun_out/g_pytest.rc) &
+(timeout 200 python -m pytest tests -m gpu -q > gpurun_out/g_pytest.log 2>&1; echo "pytest default rc $?" > gpurun_out/g_pytest.rc) &
 for n in 1 2 3 4; do
-  (CDAE_B200_LIB=$PWD/cdae_b200/_ab/lib_epi$n.so timeout 140 python -m pytest tests/test_gpu_fulldec.py tests/test_gpu_step_full_size.py -k "fulldec or full_decode" -x -q > gpurun_out/g_epi${n}_pytest.log 2>&1; echo "pytest epi$n rc $?" > gpurun_out/g_epi${n}_pytest.rc) &
+  (CDAE_B200_LIB=$PWD/cdae_b200/_ab/lib_epi$n.so timeout 150 python -m pytest tests/test_gpu_fulldec.py tests/test_gpu_step_full_size.py -k "fulldec or full_decode" -x -q > gpurun_out/g_epi${n}_pytest.log 2>&1; echo "pytest epi$n rc $?" > gpurun_out/g_epi${n}_pytest.rc) &
 done
 wait
 cat gpurun_out/g_pytest.rc gpurun_out/g_epi*_pytest.rc; tail -2 gpurun_out/g_pytest.log
