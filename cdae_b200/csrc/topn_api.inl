@@ -148,17 +148,18 @@ static int tc_pass(cdae_handle* h, const float* Wd, const int32_t* users, int64_
 // Probe pass (topn_tc.cuh, "Probe pass"): start thresholds for sweep 1 from the M items with the largest
 // mean-user score.  Leaves them in h->tc_probe_thr (one per user of the list) and returns M in *m_out, or
 // *m_out = 0 when the item table is too small for a probe to pay (fewer than 512 items) or
-// CDAE_B200_TOPN_PROBE=0.  h->tc_wb must hold the packed item side.
+// CDAE_B200_TOPN_PROBE=0 (1 = on; n >= 2 = on with up to n tiles of 256 probe items instead of 4).  h->tc_wb must hold the packed item side.
 #ifndef TOPN_PROBE_DEFAULT
 #define TOPN_PROBE_DEFAULT 0
 #endif
 static int tc_probe_thresholds(cdae_handle* h, const float* Wd, const int32_t* users, int64_t n_users, int topk, int* m_out) {
   *m_out = 0;
   const char* env = getenv("CDAE_B200_TOPN_PROBE");   // read per call: tests switch it inside one process
-  const bool on = env ? atoi(env) != 0 : TOPN_PROBE_DEFAULT != 0;
-  if (!on || h->I < 512 || n_users <= 0 || h->I >= 0x7fffffff) return 0;
+  const int knob = env ? atoi(env) : TOPN_PROBE_DEFAULT;     // 0 off, 1 on (up to 4 tiles of 256 items), n >= 2: up to n tiles
+  if (knob <= 0 || h->I < 512 || n_users <= 0 || h->I >= 0x7fffffff) return 0;
   const int K = h->K, Kp = (int)round_up(K + 2, tc::KBLK), KB = Kp / tc::KBLK;
-  const int M = tc::TILE_I * (int)std::min<int64_t>(4, std::max<int64_t>(1, h->I / 2048));   // 256 .. 1024, <= I / 2
+  const int max_tiles = knob == 1 ? 4 : std::min(knob, 32);
+  const int M = tc::TILE_I * (int)std::min<int64_t>(max_tiles, std::max<int64_t>(1, h->I / 2048));   // 256 .., <= I / 2
   const int64_t n_pad = round_up(n_users, tc::TILE_U);
   const int64_t words = M / 32;
   const int I = (int)h->I;

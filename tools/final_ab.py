@@ -81,7 +81,7 @@ def topn():
     for ep in range(3):
         m.train_one_iteration(seed=1, epoch=ep)
     lists = {}
-    for probe in ("0", "1"):
+    for probe in ("0", "1", "8", "16", "2"):
         os.environ["CDAE_B200_TOPN_PROBE"] = probe
         m.pre_recommend(10)
         m.profile(True)
@@ -100,7 +100,7 @@ def topn():
                    per_class_ms={k: round(prof[k][0] / reps, 4) for k in keys if k in prof and prof[k][1]},
                    users_per_s=U / (sum(prof[k][0] for k in keys if k in prof) / reps / 1e3))
         print(json.dumps(out), flush=True)
-    print(json.dumps(dict(what="topn_lists_equal", equal=bool(np.array_equal(lists["0"], lists["1"])))), flush=True)
+    print(json.dumps(dict(what="topn_lists_equal", equal=bool(all(np.array_equal(lists["0"], v) for v in lists.values())))), flush=True)
 
 
 if __name__ == "__main__":
