@@ -490,7 +490,7 @@ def tensor_roofline(c, prof, steps, users_rank, step_ms, pk):
             "traffic": ncu_traffic("fd_gemm_kernel")[0]}
 
 
-def topn_section(m, c, U, pk):
+def topn_section(m, c, U, pk, sm_mhz=None, sms=148):
     """Secondary measurement (not part of the timed training step): CDAE::recommend for all users,
     i.e. the full-item decode on tcgen05 (csrc/topn_tc.cuh), against the measured bf16 peak."""
     K, ITEMS = c["K"], c["items"]
@@ -510,6 +510,15 @@ def topn_section(m, c, U, pk):
             "users_per_s": U / (sum(prof[k][0] for k in ("gather", "activate", "topn", "topn_pack", "topn_rerank", "topn_exact")) / reps / 1e3),
             "candidate_kernel_ms": ms, "verified_users": verified, "redone_exact_users": redone,
             "probe_items": m.topn_probe_items(),               # > 0: sweep 1 started from probe thresholds (both launches are in candidate_kernel_ms)
+            # At small K the sweep is not tensor-bound: every score is read out of TMEM once, and the guide's measured
+            # TMEM read rate (B300_MICROARCH.md "LDTM throughput": 64 B per clock per SM, measured on sm_103 — not
+            # re-measured on this B200) is the floor: U * I * 4 bytes against SMs * 64 B * SM clock.
+            "roofline_epilogue": (lambda clk: {"bound": "tmem_read", "unit": "GB/s",
+                                               "achieved": U * ITEMS * 4.0 / (ms / 1e3) / 1e9 if ms > 0 else None,
+                                               "peak": sms * 64.0 * clk * 1e6 / 1e9,
+                                               "peak_source": "B300_MICROARCH.md LDTM 64 B/clk/SM x %d SMs x %.0f MHz (guide constant, not re-measured)" % (sms, clk),
+                                               "frac": (U * ITEMS * 4.0 / (ms / 1e3) / 1e9) / (sms * 64.0 * clk * 1e6 / 1e9) if ms > 0 else None})(
+                float(sm_mhz or 1965.0)),
             "roofline": {"bound": "tensor", "kernel": "topn_tc_kernel<%d>" % (kp // 64),
                          "achieved": alg / (ms / 1e3) / 1e12 if ms > 0 else None, "peak": pk["tf_burst"],
                          "peak_source": pk["source"] + ", burst", "unit": "TFLOP/s",
@@ -553,7 +562,8 @@ def run_ours(args):
     c = CONFIGS[primary]
     if rank == 0:
         if world == 1 and primary == "B" and not args.no_topn:
-            line["topn"] = topn_section(m, c, c["users_per_gpu"], peaks())
+            line["topn"] = topn_section(m, c, c["users_per_gpu"], peaks(),
+                                        sm_mhz=(line.get("clocks") or {}).get("sm_mhz"), sms=ctx.sms)
     m.close()
     ctx.last_model = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

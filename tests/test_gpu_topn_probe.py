@@ -21,15 +21,22 @@ def probe_on(monkeypatch):
     monkeypatch.setenv("CDAE_B200_TOPN_PROBE", "1")
 
 
-@pytest.mark.parametrize("K,I,expect_m", [(10, 1100, 256), (50, 1100, 256), (100, 2600, 256), (256, 1100, 256),
-                                          (50, 5000, 512), (20, 9000, 1024)])
-def test_lists_match_oracle_with_probe(orc, probe_on, K, I, expect_m):
+def probe_size(I, knob=1):
+    """tc_probe_thresholds (topn_api.inl): 256-item tiles, one per 2048 items, at most 4 (knob n >= 2: at most n)."""
+    if I < 512:
+        return 0
+    return 256 * min(4 if knob == 1 else knob, max(1, I // 2048))
+
+
+@pytest.mark.parametrize("K,I,U,mean", [(10, 1100, 300, 14.0), (50, 1100, 300, 14.0), (100, 2600, 300, 14.0),
+                                        (256, 1100, 300, 14.0), (50, 5000, 600, 30.0), (20, 9000, 900, 40.0)])
+def test_lists_match_oracle_with_probe(orc, probe_on, K, I, U, mean):
     cfg = orc.default_config(loss="CE", num_dim=K, asymmetric=(K % 20 == 0))
-    data = cases.small_dataset(U=300, I=I, mean=14.0, seed=300 + K)
+    data = cases.small_dataset(U=U, I=I, mean=mean, seed=300 + K)
     p = cases.random_params(data["U"], data["I"], K, K, cfg["asymmetric"], True)
-    m, (path, verified, redone) = check_lists(orc, cfg, data, p)
+    m, (path, verified, redone) = check_lists(orc, cfg, data, p, users=range(0, data["U"], max(1, data["U"] // 300)))
     assert path == 1 and verified + redone == data["U"]
-    assert m.topn_probe_items() == expect_m
+    assert m.topn_probe_items() == probe_size(data["I"])
     assert verified >= (0.9 if K < 255 else 0.6) * data["U"]
 
 
@@ -39,6 +46,21 @@ def test_probe_is_skipped_for_small_item_tables(orc, probe_on):
     p = cases.random_params(data["U"], data["I"], 20, 1, False, True)
     m, (path, _, _) = check_lists(orc, cfg, data, p)
     assert path == 1 and m.topn_probe_items() == 0
+
+
+def test_probe_tile_knob(orc, monkeypatch):
+    """CDAE_B200_TOPN_PROBE=n >= 2 allows up to n tiles; the lists do not depend on it."""
+    cfg = orc.default_config(loss="CE", num_dim=20)
+    data = cases.small_dataset(U=900, I=9000, mean=40.0, seed=77)
+    p = cases.random_params(data["U"], data["I"], 20, 2, False, True)
+    ref = None
+    for knob in ("0", "1", "2", "8"):
+        monkeypatch.setenv("CDAE_B200_TOPN_PROBE", knob)
+        m = gpu_model(cfg, data["U"], data["I"], data["train_row_ptr"], data["train_col"], p)
+        ids, _ = m.recommend_all(10)
+        assert m.topn_probe_items() == (0 if knob == "0" else probe_size(data["I"], int(knob)))
+        ref = ids if ref is None else ref
+        assert np.array_equal(ids, ref), knob
 
 
 def test_trained_model_same_lists_with_and_without_probe(orc, monkeypatch):
@@ -60,7 +82,7 @@ def test_trained_model_same_lists_with_and_without_probe(orc, monkeypatch):
     assert m0.topn_probe_items() == 0
     monkeypatch.setenv("CDAE_B200_TOPN_PROBE", "1")
     m1, (path, verified, redone) = check_lists(orc, cfg, data, trained)
-    assert path == 1 and verified + redone == U and m1.topn_probe_items() == 256
+    assert path == 1 and verified + redone == U and m1.topn_probe_items() == probe_size(I)
     ids1, sc1 = m1.recommend_all(10)
     assert np.array_equal(ids0, ids1)
     np.testing.assert_allclose(sc0, sc1, rtol=0, atol=0)

@@ -59,6 +59,18 @@ def main(path):
         for h in tensor_cols:
             if r[idx[h]] not in ("", "n/a", "0"):
                 print("    %-16s %s %s" % (h[:60], r[idx[h]], units[idx[h]]))
+        # execution pipes above 2 % (which pipe an issue-bound kernel is bound by)
+        pipes = []
+        for h in hdr:
+            if (h.startswith("sm__inst_executed_pipe_") or (h.startswith("sm__pipe_") and "cycles_active" in h)) and \
+                    h.endswith(".avg.pct_of_peak_sustained_active") and "tensor" not in h and r[idx[h]] not in ("", "n/a"):
+                try:
+                    pipes.append((float(r[idx[h]].replace(",", "")), h))
+                except ValueError:
+                    pass
+        for v, h in sorted(pipes, reverse=True)[:8]:
+            if v >= 2.0:
+                print("    pipe  %-44s %.1f %%" % (h.replace(".avg.pct_of_peak_sustained_active", ""), v))
         # warp-stall breakdown: cycles a warp waits per issued instruction, by reason (top 6)
         stalls = []
         for h in hdr:
