@@ -22,10 +22,11 @@ def probe_on(monkeypatch):
 
 
 def probe_size(I, knob=1):
-    """tc_probe_thresholds (topn_api.inl): 256-item tiles, one per 2048 items, at most 4 (knob n >= 2: at most n)."""
-    if I < 512:
+    """tc_probe_thresholds (topn_api.inl): 256-item tiles, one per 2048 items, at most 4 (knob n >= 2: at most
+    min(n, 32))."""
+    if I < 512 or knob <= 0:
         return 0
-    return 256 * min(4 if knob == 1 else knob, max(1, I // 2048))
+    return 256 * min(4 if knob == 1 else min(knob, 32), max(1, I // 2048))
 
 
 @pytest.mark.parametrize("K,I,U,mean", [(10, 1100, 300, 14.0), (50, 1100, 300, 14.0), (100, 2600, 300, 14.0),
