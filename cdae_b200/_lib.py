@@ -108,6 +108,8 @@ SIGNATURES = {
     "cdae_dataset_csr": (C.c_int, [C.c_void_p, C.c_int32, i64p, i32p]),
     "cdae_dataset_raw_id": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_char_p)]),
     "cdae_dataset_free": (C.c_int, [C.c_void_p]),
+    "cdae_dataset_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cdae_dataset_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "cdae_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cdae_load": (C.c_int, [C.c_void_p, C.c_char_p]),
 }

@@ -2,8 +2,8 @@
 // N2, N3), included at the end of api.cu.  Pure C++ (no device work): the text file the reference
 // reads with Data::load(..., RECSYS, ...) goes straight to the CSR cdae_create() takes, skipping the
 // reference's vector<Instance> of nested vectors and its hash of hashes (data-inl.hpp:45-64,
-// instance.hpp:94-225, recsys_model_base.hpp:29-34), and a versioned binary checkpoint of the model
-// (the reference has none).
+// instance.hpp:94-225, recsys_model_base.hpp:29-34), a binary cache of the loaded (and split) data set — the
+// counterpart of Data::save / Data::load — and a versioned binary checkpoint of the model (the reference has none).
 #include <fstream>
 #include <string_view>
 #include <unordered_map>
@@ -179,6 +179,112 @@ int cdae_dataset_raw_id(const cdae_dataset* d, int32_t group, int64_t idx, const
 
 int cdae_dataset_free(cdae_dataset* d) {
   delete d;
+  return 0;
+}
+
+// ---- data set cache (version 1) — the counterpart of Data::save / Data::load (data.hpp:25-33, 52-60;
+// io/serialize.hpp:16-46: gzip over a boost binary archive of the instance vector and the feature-group
+// tables).  That byte format cannot be reproduced without Boost, so the cache has its own:
+//   "CDAEDS01" | u32 version | per group (users, items): u64 count, then u32 length + bytes per raw id |
+//   u64 instances, i32 user ids, i32 item ids (file order, duplicates kept) | u8 split_done |
+//   if split: per part (train, test): u64 nnz, i64 row_ptr[U + 1], i32 col[nnz]
+// The CSR of all pairs is rebuilt on load (it is a function of the instances); the split is stored, so a CPU
+// baseline run and a GPU run can share one split without sharing a seed convention.
+static const char kDsMagic[8] = {'C', 'D', 'A', 'E', 'D', 'S', '0', '1'};
+static const uint32_t kDsVersion = 1;
+
+int cdae_dataset_save(const cdae_dataset* d, const char* path) {
+  if (!d || !path) return set_error(CDAE_E_INVALID, "NULL argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) return set_error(CDAE_E_INVALID, "cannot open %s for writing", path);
+  bool ok = fwrite(kDsMagic, 1, 8, f) == 8 && fwrite(&kDsVersion, sizeof(kDsVersion), 1, f) == 1;
+  for (int g = 0; g < 2 && ok; ++g) {
+    const uint64_t n = d->raw[g].size();
+    ok = fwrite(&n, sizeof(n), 1, f) == 1;
+    for (size_t k = 0; k < d->raw[g].size() && ok; ++k) {
+      const uint32_t len = (uint32_t)d->raw[g][k].size();
+      ok = fwrite(&len, sizeof(len), 1, f) == 1 && (len == 0 || fwrite(d->raw[g][k].data(), 1, len, f) == len);
+    }
+  }
+  const uint64_t n_inst = d->pu.size();
+  ok = ok && fwrite(&n_inst, sizeof(n_inst), 1, f) == 1;
+  if (n_inst) ok = ok && fwrite(d->pu.data(), sizeof(int32_t), n_inst, f) == n_inst && fwrite(d->pi.data(), sizeof(int32_t), n_inst, f) == n_inst;
+  const uint8_t split = d->split_done ? 1 : 0;
+  ok = ok && fwrite(&split, 1, 1, f) == 1;
+  for (int w = 1; w <= 2 && ok && split; ++w) {
+    const uint64_t nnz = d->col[w].size();
+    ok = fwrite(&nnz, sizeof(nnz), 1, f) == 1 && fwrite(d->rp[w].data(), sizeof(int64_t), d->rp[w].size(), f) == d->rp[w].size() &&
+         (nnz == 0 || fwrite(d->col[w].data(), sizeof(int32_t), nnz, f) == nnz);
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return set_error(CDAE_E_INVALID, "short write to %s", path);
+  return 0;
+}
+
+int cdae_dataset_load(const char* path, cdae_dataset** out) {
+  if (!path || !out) return set_error(CDAE_E_INVALID, "NULL argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_error(CDAE_E_INVALID, "cannot open %s", path);
+  cdae_dataset* d = new cdae_dataset();
+  auto fail = [&](const char* what) {
+    fclose(f);
+    delete d;
+    return set_error(CDAE_E_INVALID, "%s: %s", path, what);
+  };
+  // sizes in the file are checked against what is left of it before anything is allocated
+  fseek(f, 0, SEEK_END);
+  const long file_size = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  auto left = [&]() -> uint64_t { return (uint64_t)(file_size - ftell(f)); };
+  char magic[8];
+  uint32_t version = 0;
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kDsMagic, 8) != 0) return fail("not a cdae_b200 data set cache");
+  if (fread(&version, sizeof(version), 1, f) != 1 || version != kDsVersion) return fail("unsupported cache version");
+  for (int g = 0; g < 2; ++g) {
+    uint64_t n = 0;
+    if (fread(&n, sizeof(n), 1, f) != 1 || n > left() / sizeof(uint32_t) || n >= 0x7fffffffull) return fail("truncated (id table)");
+    d->raw[g].resize((size_t)n);
+    for (uint64_t k = 0; k < n; ++k) {
+      uint32_t len = 0;
+      if (fread(&len, sizeof(len), 1, f) != 1 || len > left()) return fail("truncated (raw id)");
+      d->raw[g][(size_t)k].resize(len);
+      if (len && fread(&d->raw[g][(size_t)k][0], 1, len, f) != len) return fail("truncated (raw id)");
+    }
+  }
+  const int64_t U = (int64_t)d->raw[0].size(), I = (int64_t)d->raw[1].size();
+  uint64_t n_inst = 0;
+  if (fread(&n_inst, sizeof(n_inst), 1, f) != 1 || n_inst > left() / (2 * sizeof(int32_t))) return fail("truncated (instances)");
+  d->pu.resize((size_t)n_inst);
+  d->pi.resize((size_t)n_inst);
+  if (n_inst && (fread(d->pu.data(), sizeof(int32_t), n_inst, f) != n_inst || fread(d->pi.data(), sizeof(int32_t), n_inst, f) != n_inst))
+    return fail("truncated (instances)");
+  for (uint64_t k = 0; k < n_inst; ++k)
+    if (d->pu[(size_t)k] < 0 || d->pu[(size_t)k] >= U || d->pi[(size_t)k] < 0 || d->pi[(size_t)k] >= I) return fail("instance id out of range");
+  uint8_t split = 0;
+  if (fread(&split, 1, 1, f) != 1 || split > 1) return fail("truncated (split flag)");
+  for (int w = 1; w <= 2 && split; ++w) {
+    uint64_t nnz = 0;
+    if (fread(&nnz, sizeof(nnz), 1, f) != 1 || nnz > left() / sizeof(int32_t) || (uint64_t)(U + 1) > left() / sizeof(int64_t))
+      return fail("truncated (split part)");
+    d->rp[w].resize((size_t)U + 1);
+    d->col[w].resize((size_t)nnz);
+    if (fread(d->rp[w].data(), sizeof(int64_t), (size_t)U + 1, f) != (size_t)U + 1 ||
+        (nnz && fread(d->col[w].data(), sizeof(int32_t), nnz, f) != nnz))
+      return fail("truncated (split part)");
+    // the same invariants cdae_create checks: monotone row_ptr ending at nnz, ids in range, rows strictly ascending
+    if (d->rp[w][0] != 0 || d->rp[w][(size_t)U] != (int64_t)nnz) return fail("split part: row_ptr does not match nnz");
+    for (int64_t u = 0; u < U; ++u) {
+      if (d->rp[w][(size_t)u + 1] < d->rp[w][(size_t)u]) return fail("split part: row_ptr not monotone");
+      for (int64_t s0 = d->rp[w][(size_t)u]; s0 < d->rp[w][(size_t)u + 1]; ++s0) {
+        const int32_t c = d->col[w][(size_t)s0];
+        if (c < 0 || c >= I || (s0 > d->rp[w][(size_t)u] && d->col[w][(size_t)s0 - 1] >= c)) return fail("split part: bad row");
+      }
+    }
+  }
+  fclose(f);
+  d->split_done = split != 0;
+  build_csr(U, d->pu, d->pi, nullptr, 0, &d->rp[0], &d->col[0]);
+  *out = d;
   return 0;
 }
 

@@ -11,14 +11,26 @@ from . import _lib
 class Dataset:
     """`Data` for "user item" text files: dense ids in first-seen order (instance-inl.hpp:22-37)."""
 
-    def __init__(self, path, delimiters=" ", skip_header=False):
+    def __init__(self, path, delimiters=" ", skip_header=False, _cache=False):
         self._L = _lib.lib()
         self._h = C.c_void_p()
-        _lib.check(self._L.cdae_dataset_load_pairs(str(path).encode(), delimiters.encode(), int(skip_header),
-                                                   C.byref(self._h)))
+        if _cache:
+            _lib.check(self._L.cdae_dataset_load(str(path).encode(), C.byref(self._h)))
+        else:
+            _lib.check(self._L.cdae_dataset_load_pairs(str(path).encode(), delimiters.encode(), int(skip_header),
+                                                       C.byref(self._h)))
         u, i, n = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self._L.cdae_dataset_info(self._h, C.byref(u), C.byref(i), C.byref(n)))
         self.num_users, self.num_items, self.num_instances = u.value, i.value, n.value
+
+    def save(self, path):
+        """Data::save (data.hpp:25-33) in the library's own cache format: ids, instances and the split if made."""
+        _lib.check(self._L.cdae_dataset_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path):
+        """Data::load(cache file) (data.hpp:52-60): a data set written by save()."""
+        return cls(path, _cache=True)
 
     def close(self):
         if self._h:

@@ -217,6 +217,14 @@ int cdae_dataset_csr(const cdae_dataset* d, int32_t which, int64_t* row_ptr, int
 /* the raw string of a dense id (group 0 = users, 1 = items): FeatureGroupInfo::raw_str_map_ */
 int cdae_dataset_raw_id(const cdae_dataset* d, int32_t group, int64_t idx, const char** out);
 int cdae_dataset_free(cdae_dataset* d);
+/* Data set cache: the counterpart of Data::save / Data::load (data.hpp:25-33, 52-60;
+ * io/serialize.hpp:16-46 — gzip over a boost binary archive, a byte format that cannot be reproduced without
+ * Boost).  Own versioned binary format: raw id tables, the instances in file order and, if cdae_dataset_split
+ * has run, the train / test CSRs — so that a CPU baseline run and a GPU run share one split.  cdae_dataset_load
+ * checks every size against the file and the CSR invariants cdae_create relies on; a file that fails is
+ * CDAE_E_INVALID. */
+int cdae_dataset_save(const cdae_dataset* d, const char* path);
+int cdae_dataset_load(const char* path, cdae_dataset** out);
 
 /* Model checkpoint (the reference has none — its save/load only cover Data):
  * versioned binary file with the config, the shape and every parameter block incl. AdaGrad state

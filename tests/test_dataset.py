@@ -101,3 +101,66 @@ def test_split_rule(lib):
     assert not np.array_equal(tcol, tcol3)
     n_test_total = int(sum(int(c * 0.2) for c in users.values()))
     assert 0 < len(ecol) <= n_test_total
+
+
+def test_cache_round_trip(lib, tmp_path):
+    """cdae_dataset_save / cdae_dataset_load (SURVEY §8f N3; Data::save / Data::load, data.hpp:25-33, 52-60):
+    ids, instances and the split survive a round trip; an unsplit data set stays unsplit."""
+    from cdae_b200 import CdaeError
+    src = os.path.join(HERE, "golden", "pairs_small.txt")
+    d = lib.Dataset(src)
+    p0 = tmp_path / "unsplit.cdaeds"
+    d.save(p0)
+    e = lib.Dataset.load(p0)
+    assert (e.num_users, e.num_items, e.num_instances) == (d.num_users, d.num_items, d.num_instances)
+    for a, b in zip(d.csr("all"), e.csr("all")):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(CdaeError):
+        e.csr("train")                                           # no split was stored
+    assert [e.raw_id(0, k) for k in range(e.num_users)] == [d.raw_id(0, k) for k in range(d.num_users)]
+    assert [e.raw_id(1, k) for k in range(e.num_items)] == [d.raw_id(1, k) for k in range(d.num_items)]
+    (trp, tcol), (erp, ecol) = d.random_split_by_feature_group(0.2, seed=5)
+    p1 = tmp_path / "split.cdaeds"
+    d.save(p1)
+    e = lib.Dataset.load(p1)
+    for which, want in (("all", d.csr("all")), ("train", (trp, tcol)), ("test", (erp, ecol))):
+        got = e.csr(which)
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+    # a fresh split of the loaded set with the same seed is the same split (the instances are in file order)
+    (trp2, tcol2), _ = e.random_split_by_feature_group(0.2, seed=5)
+    np.testing.assert_array_equal(trp2, trp)
+    np.testing.assert_array_equal(tcol2, tcol)
+
+
+def test_cache_rejects_damaged_files(lib, tmp_path):
+    from cdae_b200 import CdaeError
+    d = lib.Dataset(os.path.join(HERE, "golden", "pairs_small.txt"))
+    d.random_split_by_feature_group(0.2, seed=5)
+    p = tmp_path / "ok.cdaeds"
+    d.save(p)
+    blob = p.read_bytes()
+    assert blob[:8] == b"CDAEDS01"
+    cases_ = {
+        "magic": b"XDAEDS01" + blob[8:],
+        "version": blob[:8] + (99).to_bytes(4, "little") + blob[12:],
+        "cut_ids": blob[:40],
+        "cut_instances": blob[:len(blob) // 2],
+        "cut_tail": blob[:-5],
+        "huge_count": blob[:12] + (2**62).to_bytes(8, "little") + blob[20:],
+        "empty": b"",
+    }
+    for name, b in cases_.items():
+        q = tmp_path / (name + ".cdaeds")
+        q.write_bytes(b)
+        with pytest.raises(CdaeError):
+            lib.Dataset.load(q)
+    # a column id pushed out of range in the stored test part (the last 4 bytes of the file are its last entry)
+    bad = bytearray(blob)
+    bad[-4:] = (2**30).to_bytes(4, "little")
+    q = tmp_path / "bad_col.cdaeds"
+    q.write_bytes(bytes(bad))
+    with pytest.raises(CdaeError):
+        lib.Dataset.load(q)
+    with pytest.raises(CdaeError):
+        lib.Dataset.load(tmp_path / "missing.cdaeds")
