@@ -221,16 +221,8 @@ int cdae_dataset_save(const cdae_dataset* d, const char* path) {
   return 0;
 }
 
-int cdae_dataset_load(const char* path, cdae_dataset** out) {
-  if (!path || !out) return set_error(CDAE_E_INVALID, "NULL argument");
-  FILE* f = fopen(path, "rb");
-  if (!f) return set_error(CDAE_E_INVALID, "cannot open %s", path);
-  cdae_dataset* d = new cdae_dataset();
-  auto fail = [&](const char* what) {
-    fclose(f);
-    delete d;
-    return set_error(CDAE_E_INVALID, "%s: %s", path, what);
-  };
+static int dataset_load_impl(const char* path, FILE* f, cdae_dataset* d) {
+  auto fail = [&](const char* what) { return set_error(CDAE_E_INVALID, "%s: %s", path, what); };
   // sizes in the file are checked against what is left of it before anything is allocated
   fseek(f, 0, SEEK_END);
   const long file_size = ftell(f);
@@ -281,9 +273,28 @@ int cdae_dataset_load(const char* path, cdae_dataset** out) {
       }
     }
   }
-  fclose(f);
   d->split_done = split != 0;
   build_csr(U, d->pu, d->pi, nullptr, 0, &d->rp[0], &d->col[0]);
+  return 0;
+}
+
+int cdae_dataset_load(const char* path, cdae_dataset** out) {
+  if (!path || !out) return set_error(CDAE_E_INVALID, "NULL argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return set_error(CDAE_E_INVALID, "cannot open %s", path);
+  cdae_dataset* d = nullptr;
+  int rc;
+  try {   // no exception may cross the C ABI (a damaged file can still ask for more memory than there is)
+    d = new cdae_dataset();
+    rc = dataset_load_impl(path, f, d);
+  } catch (const std::exception& e) {
+    rc = set_error(CDAE_E_INVALID, "%s: %s", path, e.what());
+  }
+  fclose(f);
+  if (rc != 0) {
+    delete d;
+    return rc;
+  }
   *out = d;
   return 0;
 }
