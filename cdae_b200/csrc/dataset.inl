@@ -5,6 +5,7 @@
 // instance.hpp:94-225, recsys_model_base.hpp:29-34), a binary cache of the loaded (and split) data set — the
 // counterpart of Data::save / Data::load — and a versioned binary checkpoint of the model (the reference has none).
 #include <fstream>
+#include <memory>
 #include <string_view>
 #include <unordered_map>
 
@@ -45,8 +46,7 @@ void build_csr(int64_t U, const std::vector<int32_t>& u, const std::vector<int32
 
 extern "C" {
 
-int cdae_dataset_load_pairs(const char* path, const char* delimiters, int32_t skip_header, cdae_dataset** out) {
-  if (!path || !out) return set_error(CDAE_E_INVALID, "NULL argument");
+static int dataset_load_pairs_impl(const char* path, const char* delimiters, int32_t skip_header, cdae_dataset** out) {
   const std::string delims = delimiters && *delimiters ? delimiters : " ";
   std::ifstream f(path, std::ios::binary | std::ios::ate);
   if (!f) return set_error(CDAE_E_INVALID, "cannot open %s", path);
@@ -57,7 +57,8 @@ int cdae_dataset_load_pairs(const char* path, const char* delimiters, int32_t sk
   bool is_delim[256] = {false};
   for (unsigned char c : delims) is_delim[c] = true;
 
-  cdae_dataset* d = new cdae_dataset();
+  std::unique_ptr<cdae_dataset> holder(new cdae_dataset());
+  cdae_dataset* d = holder.get();
   std::unordered_map<std::string_view, int32_t> idx[2];   // FeatureGroupInfo::idx_map_: ids in first-seen order
   idx[0].reserve(1 << 16);
   idx[1].reserve(1 << 16);
@@ -87,7 +88,6 @@ int cdae_dataset_load_pairs(const char* path, const char* delimiters, int32_t sk
         ++nt;
       }
       if (nt != 2) {                                       // the app's parser CHECK_EQ(rets.size(), 2), yelp.cpp:62
-        delete d;
         return set_error(CDAE_E_INVALID, "%s: line %zu has %d fields, expected 2 (the reference CHECK-aborts, yelp.cpp:62)",
                          path, line_num, nt);
       }
@@ -112,8 +112,17 @@ int cdae_dataset_load_pairs(const char* path, const char* delimiters, int32_t sk
     for (auto sv : first[g]) d->raw[g].emplace_back(sv);
   }
   build_csr((int64_t)d->raw[0].size(), d->pu, d->pi, nullptr, 0, &d->rp[0], &d->col[0]);
-  *out = d;
+  *out = holder.release();
   return 0;
+}
+
+int cdae_dataset_load_pairs(const char* path, const char* delimiters, int32_t skip_header, cdae_dataset** out) {
+  if (!path || !out) return set_error(CDAE_E_INVALID, "NULL argument");
+  try {   // no exception may cross the C ABI
+    return dataset_load_pairs_impl(path, delimiters, skip_header, out);
+  } catch (const std::exception& e) {
+    return set_error(CDAE_E_INVALID, "%s: %s", path, e.what());
+  }
 }
 
 int cdae_dataset_info(const cdae_dataset* d, int64_t* users, int64_t* items, int64_t* instances) {
@@ -124,8 +133,7 @@ int cdae_dataset_info(const cdae_dataset* d, int64_t* users, int64_t* items, int
   return 0;
 }
 
-int cdae_dataset_split(cdae_dataset* d, double test_ratio, uint64_t seed) {
-  if (!d || !(test_ratio >= 0. && test_ratio <= 1.)) return set_error(CDAE_E_INVALID, "bad argument");
+static int dataset_split_impl(cdae_dataset* d, double test_ratio, uint64_t seed) {
   // Data::random_split_by_feature_group(train, test, 0, ratio), data-inl.hpp:231-272: every user's
   // INSTANCES are shuffled and the first floor(n * ratio) go to test.  The shuffle is a Fisher-Yates
   // over the user's instances in file order driven by Philox4x32(seed, {uid, k, 0, 0x5B117}) — the
@@ -153,6 +161,16 @@ int cdae_dataset_split(cdae_dataset* d, double test_ratio, uint64_t seed) {
   build_csr(U, d->pu, d->pi, &sel, 2, &d->rp[2], &d->col[2]);
   d->split_done = true;
   return 0;
+}
+
+int cdae_dataset_split(cdae_dataset* d, double test_ratio, uint64_t seed) {
+  if (!d || !(test_ratio >= 0. && test_ratio <= 1.)) return set_error(CDAE_E_INVALID, "bad argument");
+  try {   // no exception may cross the C ABI
+    return dataset_split_impl(d, test_ratio, seed);
+  } catch (const std::exception& e) {
+    d->split_done = false;
+    return set_error(CDAE_E_INVALID, "split: %s", e.what());
+  }
 }
 
 int cdae_dataset_nnz(const cdae_dataset* d, int32_t which, int64_t* nnz) {
